@@ -1,0 +1,353 @@
+// 254-bit prime-field arithmetic for BN128 (Fq = base field p, Fr = scalar field r)
+// as 8 x 32-bit limbs in Montgomery form (R = 2^256), written for sm_100a.
+//
+// Replaces the reference's BigInt-backed FiniteFieldElement ops
+// (myzkp/src/modules/algebra/field.rs:157-183 add/sub/mul + `% modulus`,
+//  field.rs:210-237 inverse) on the KZG hot path.  Values are always kept
+// canonical in [0, m), so equality of limbs == the reference's equality of
+// sanitized values (field.rs:290-294).
+//
+// The multiply is an even/odd-column CIOS: 64-bit partial products are
+// accumulated with mad.lo.cc/madc.hi.cc pairs, which ptxas fuses into
+// IMAD.WIDE.U32(.X) with predicate carries on sm_100a (checked with
+// cuobjdump -sass: ~120 IMAD.WIDE + 8 IMAD.HI + 9 IMAD per multiply).
+//
+// The same header compiles for the host (g++) with an emulated carry flag so
+// that tests can run the exact device algorithms on the CPU
+// (tests/emul/); the product library never uses that path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MZ_HD __host__ __device__ __forceinline__
+#define MZ_D __device__ __forceinline__
+#else
+#define MZ_HD inline
+#define MZ_D inline
+#endif
+
+namespace mz {
+
+// ---------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define MZ_ASM asm volatile
+MZ_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MZ_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+MZ_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+MZ_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MZ_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MZ_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MZ_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MZ_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// host emulation of the PTX condition-code register (tests only)
+static thread_local uint32_t g_cf = 0;
+inline uint32_t emu_add(uint32_t a, uint32_t b, uint32_t cin, bool set) {
+  uint64_t s = (uint64_t)a + b + cin;
+  if (set) g_cf = (uint32_t)(s >> 32);
+  return (uint32_t)s;
+}
+inline uint32_t emu_sub(uint32_t a, uint32_t b, uint32_t bin, bool set) {
+  uint64_t s = (uint64_t)a - b - bin;
+  if (set) g_cf = (uint32_t)((s >> 32) & 1);  // borrow
+  return (uint32_t)s;
+}
+inline uint32_t add_cc(uint32_t a, uint32_t b) { return emu_add(a, b, 0, true); }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { return emu_add(a, b, g_cf, true); }
+inline uint32_t addc(uint32_t a, uint32_t b) { return emu_add(a, b, g_cf, false); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, 0, true); }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, true); }
+inline uint32_t subc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, false); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, 0, true); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, g_cf, true); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, 0, true); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, true); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, false); }
+#endif
+
+// ---------------------------------------------------------------------------
+// moduli (curve/bn128.rs:19-22, field.rs:428-431)
+// ---------------------------------------------------------------------------
+#define MZ_LIMBS8(name, a0, a1, a2, a3, a4, a5, a6, a7)                          \
+  static MZ_HD constexpr uint32_t name(int i) {                                  \
+    return i == 0 ? a0 : i == 1 ? a1 : i == 2 ? a2 : i == 3 ? a3 : i == 4 ? a4  \
+         : i == 5 ? a5 : i == 6 ? a6 : a7;                                       \
+  }
+
+struct FqParams {  // base field p
+  MZ_LIMBS8(mod, 0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+            0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u)
+  static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32
+  // R = 2^256 mod p (Montgomery one)
+  MZ_LIMBS8(one, 0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+            0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u)
+  // R^2 = 2^512 mod p
+  MZ_LIMBS8(r2, 0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+            0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u)
+};
+struct FrParams {  // scalar field r
+  MZ_LIMBS8(mod, 0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+            0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u)
+  static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+  MZ_LIMBS8(one, 0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+            0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u)
+  MZ_LIMBS8(r2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+            0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u)
+};
+
+template <class PR>
+MZ_HD constexpr uint32_t mod_limb(int i) { return PR::mod(i); }
+
+// ---------------------------------------------------------------------------
+// field element
+// ---------------------------------------------------------------------------
+template <class PR>
+struct Fe {
+  uint32_t v[8];
+
+  static MZ_HD Fe zero() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  static MZ_HD Fe one() {  // Montgomery form of 1
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = PR::one(i);
+    return r;
+  }
+  static MZ_HD Fe r2() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = PR::r2(i);
+    return r;
+  }
+  MZ_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  MZ_HD bool operator==(const Fe& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  MZ_HD bool operator!=(const Fe& b) const { return !(*this == b); }
+};
+
+// r = a - m if a >= m else a   (a < 2m)
+template <class PR>
+MZ_HD void fe_reduce_once(Fe<PR>& a) {
+  uint32_t t[8];
+  t[0] = sub_cc(a.v[0], mod_limb<PR>(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) t[i] = subc_cc(a.v[i], mod_limb<PR>(i));
+  uint32_t borrow = subc(0, 0);  // 0xffffffff if a < m
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+// true iff a (any 256-bit value) < modulus
+template <class PR>
+MZ_HD bool fe_is_canonical(const Fe<PR>& a) {
+  (void)sub_cc(a.v[0], mod_limb<PR>(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) (void)subc_cc(a.v[i], mod_limb<PR>(i));
+  return subc(0, 0) != 0;
+}
+
+template <class PR>
+MZ_HD Fe<PR> fe_add(const Fe<PR>& a, const Fe<PR>& b) {
+  Fe<PR> r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  r.v[7] = addc(a.v[7], b.v[7]);  // both < 2^254: no carry out
+  fe_reduce_once(r);
+  return r;
+}
+
+template <class PR>
+MZ_HD Fe<PR> fe_sub(const Fe<PR>& a, const Fe<PR>& b) {
+  Fe<PR> r;
+  r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = subc(0, 0);  // all-ones if a < b
+  r.v[0] = add_cc(r.v[0], borrow & mod_limb<PR>(0));
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], borrow & mod_limb<PR>(i));
+  r.v[7] = addc(r.v[7], borrow & mod_limb<PR>(7));
+  return r;
+}
+
+template <class PR>
+MZ_HD Fe<PR> fe_neg(const Fe<PR>& a) {
+  Fe<PR> r;
+  uint32_t nz = a.is_zero() ? 0u : 0xffffffffu;
+  r.v[0] = sub_cc(mod_limb<PR>(0) & nz, a.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = subc_cc(mod_limb<PR>(i) & nz, a.v[i]);
+  r.v[7] = subc(mod_limb<PR>(7) & nz, a.v[7]);
+  return r;
+}
+
+template <class PR>
+MZ_HD Fe<PR> fe_dbl(const Fe<PR>& a) { return fe_add(a, a); }
+
+// --- Montgomery multiply ----------------------------------------------------
+// Accumulators: E[k] holds column k, O[k] holds column k+1 of the running sum.
+// One row adds a*b_i and m*modulus, after which column 0 is zero and the
+// roles swap (old O becomes the new E; old E shifted by two limbs the new O).
+namespace detail {
+
+// acc[j..j+1] += a[j] * bi for even j, one carry chain, carry left in CF
+template <class A>
+MZ_HD void row_mad_even(uint32_t* acc, const A& a, uint32_t bi) {
+  acc[0] = mad_lo_cc(a(0), bi, acc[0]);
+  acc[1] = madc_hi_cc(a(0), bi, acc[1]);
+#pragma unroll
+  for (int j = 2; j < 8; j += 2) {
+    acc[j] = madc_lo_cc(a(j), bi, acc[j]);
+    acc[j + 1] = madc_hi_cc(a(j), bi, acc[j + 1]);
+  }
+}
+// acc[j-1..j] += a[j] * bi for odd j (acc is the odd-column array)
+template <class A>
+MZ_HD void row_mad_odd(uint32_t* acc, const A& a, uint32_t bi) {
+  acc[0] = mad_lo_cc(a(1), bi, acc[0]);
+  acc[1] = madc_hi_cc(a(1), bi, acc[1]);
+#pragma unroll
+  for (int j = 2; j < 8; j += 2) {
+    acc[j] = madc_lo_cc(a(j + 1), bi, acc[j]);
+    acc[j + 1] = madc_hi_cc(a(j + 1), bi, acc[j + 1]);
+  }
+}
+// new odd-column array from the old even array shifted down two limbs, plus
+// the odd-limb products; consumes the incoming CF (from folding old column 1)
+template <class A>
+MZ_HD void row_shift_mad_odd(uint32_t* acc, const A& a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < 6; j += 2) {
+    acc[j] = madc_lo_cc(a(j + 1), bi, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(a(j + 1), bi, acc[j + 3]);
+  }
+  acc[6] = madc_lo_cc(a(7), bi, 0);
+  acc[7] = madc_hi(a(7), bi, 0);
+}
+
+template <class PR>
+struct ModAcc {
+  MZ_HD uint32_t operator()(int i) const { return mod_limb<PR>(i); }
+};
+struct ArrAcc {
+  const uint32_t* p;
+  MZ_HD uint32_t operator()(int i) const { return p[i]; }
+};
+
+template <class PR>
+MZ_HD void mont_row(uint32_t* E, uint32_t* O, const ArrAcc& a, uint32_t bi, bool first) {
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      O[j] = mul_lo(a(j + 1), bi);
+      O[j + 1] = mul_hi(a(j + 1), bi);
+      E[j] = mul_lo(a(j), bi);
+      E[j + 1] = mul_hi(a(j), bi);
+    }
+  } else {
+    // E is the previous row's odd array (already in place); O is the previous
+    // even array whose column 0 is zero and column 1 (O[1]) folds into E[0].
+    E[0] = add_cc(E[0], O[1]);
+    row_shift_mad_odd(O, a, bi);
+    row_mad_even(E, a, bi);
+    O[7] = addc(O[7], 0);
+  }
+  uint32_t m = mul_lo(E[0], PR::INV);
+  row_mad_odd(O, ModAcc<PR>(), m);  // cannot carry out (sum < 2^256 * 2^32)
+  row_mad_even(E, ModAcc<PR>(), m);
+  O[7] = addc(O[7], 0);
+}
+
+}  // namespace detail
+
+template <class PR>
+MZ_HD Fe<PR> fe_mul(const Fe<PR>& a, const Fe<PR>& b) {
+  uint32_t E[8], O[8];
+  detail::ArrAcc aa{a.v};
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    detail::mont_row<PR>(E, O, aa, b.v[i], i == 0);
+    detail::mont_row<PR>(O, E, aa, b.v[i + 1], false);
+  }
+  // result column k = E[k] + O[k+1]
+  Fe<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  fe_reduce_once(r);
+  return r;
+}
+
+template <class PR>
+MZ_HD Fe<PR> fe_sqr(const Fe<PR>& a) { return fe_mul(a, a); }
+
+template <class PR>
+MZ_HD Fe<PR> fe_to_mont(const Fe<PR>& a) { return fe_mul(a, Fe<PR>::r2()); }
+
+template <class PR>
+MZ_HD Fe<PR> fe_from_mont(const Fe<PR>& a) {
+  Fe<PR> one_raw = Fe<PR>::zero();
+  one_raw.v[0] = 1;
+  return fe_mul(a, one_raw);
+}
+
+// a^e for a small (<= 64-bit) public exponent; a in Montgomery form
+template <class PR>
+MZ_HD Fe<PR> fe_pow_u64(const Fe<PR>& a, uint64_t e) {
+  Fe<PR> r = Fe<PR>::one();
+  Fe<PR> base = a;
+  while (e) {
+    if (e & 1) r = fe_mul(r, base);
+    base = fe_sqr(base);
+    e >>= 1;
+  }
+  return r;
+}
+
+// Fermat inverse a^(m-2); inverse(0) = 0, as the reference's ext-Euclid
+// returns 0 for 0 (field.rs:210-237 with utils.rs:52-81).
+template <class PR>
+MZ_HD Fe<PR> fe_inv(const Fe<PR>& a) {
+  // exponent m - 2, scanned MSB first
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = mod_limb<PR>(i);
+  e[0] -= 2;  // low limb of both moduli is >= 2
+  Fe<PR> r = Fe<PR>::one();
+  for (int i = 7; i >= 0; i--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      r = fe_sqr(r);
+      if ((e[i] >> bit) & 1) r = fe_mul(r, a);
+    }
+  }
+  return r;
+}
+
+typedef Fe<FqParams> Fq;
+typedef Fe<FrParams> Fr;
+
+}  // namespace mz

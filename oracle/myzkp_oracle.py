@@ -1,0 +1,587 @@
+"""CPU oracle for the MyZKP KZG prover hot path (BN128).
+
+TEST INFRASTRUCTURE ONLY.  This module is the *checker*, never the product:
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import it.  The product path (myzkp_b200/) never does and
+fails loudly when its CUDA library is missing.
+
+It restates, line by line and on Python integers (== num-bigint BigInt
+semantics; num-bigint = "0.4", myzkp/Cargo.toml:7, un-vendored, exact integer
+arithmetic), the reference functions the hot path consists of.  Citations are
+relative to /root/reference/myzkp/src/modules/algebra/.
+
+Parity pinning: the reference cannot be compiled here (Rust toolchain absent)
+and its own KZG tests are pairing-verified property tests with an unseeded
+random alpha (kzg.rs:152-175), so commitment coordinates are *not* pinned by
+the reference.  What is pinned (tests/test_oracle_kats.py): every known-answer
+test the reference holds under this path - bn128.rs:285-301 (test_g1),
+bn128.rs:240-251 (test_fq), field.rs:443-550, polynomial.rs:727-768,805-821,
+cuda/test_fr.cu:5-42, gemini.rs:288-307 / book gemini.md:311-328 - plus the
+public EIP-196 value of 2G and the algebraic identity C == [f(alpha)]G.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+# --- constants: curve/bn128.rs:19-23, field.rs:428-431 ----------------------
+P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+CURVE_A = 0  # bn128.rs:23 define_myzkp_curve_type!(BN128Curve, "0", "3")
+CURVE_B = 3
+
+
+def _trunc_rem(a: int, m: int) -> int:
+    """Rust/num-bigint `%`: truncated remainder, sign follows the dividend."""
+    r = abs(a) % m
+    return -r if a < 0 else r
+
+
+def _trunc_div(a: int, b: int) -> int:
+    """Rust/num-bigint `/`: quotient truncated toward zero."""
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q
+
+
+def extended_euclidean(a: int, b: int) -> Tuple[int, int, int]:
+    """utils.rs:52-81."""
+    r0, r1 = a, b
+    s0, s1 = 1, 0
+    t0, t1 = 0, 1
+    while r1 != 0:
+        q = _trunc_div(r0, r1)
+        r = _trunc_rem(r0, r1)
+        r0, r1 = r1, r
+        s0, s1 = s1, s0 - q * s1
+        t0, t1 = t1, t0 - q * t1
+    return r0, s0, t0
+
+
+def mod_pow(x: int, y: int, modulus: int) -> int:
+    """utils.rs:108-137 (non-negative exponent branch)."""
+    assert y >= 0
+    base = _trunc_rem(x, modulus)
+    result = 1
+    e = y
+    while e > 0:
+        if e & 1:
+            result = _trunc_rem(result * base, modulus)
+        e >>= 1
+        base = _trunc_rem(base * base, modulus)
+    return result
+
+
+class FE:
+    """FiniteFieldElement<M> (field.rs:87-91): `value` may be negative, exactly
+    as in the reference (new() uses truncated `%`, field.rs:102-110)."""
+
+    __slots__ = ("value",)
+    MOD = 0
+
+    def __init__(self, value: int):
+        self.value = _trunc_rem(int(value), self.MOD)  # field.rs:104-105
+
+    # Ring (field.rs:157-195)
+    def add_ref(self, o: "FE") -> "FE":
+        return type(self)(self.value + o.value)
+
+    def sub_ref(self, o: "FE") -> "FE":
+        return type(self)(self.value - o.value)
+
+    def mul_ref(self, o: "FE") -> "FE":
+        return type(self)(self.value * o.value)
+
+    def pow(self, n: int) -> "FE":
+        return type(self)(mod_pow(self.value, n, self.MOD))
+
+    @classmethod
+    def from_value(cls, v: int) -> "FE":
+        return cls(v)
+
+    def get_value(self) -> int:
+        return self.value
+
+    @classmethod
+    def zero(cls) -> "FE":
+        return cls(0)
+
+    @classmethod
+    def one(cls) -> "FE":
+        return cls(1)
+
+    # Field (field.rs:210-270)
+    def inverse(self) -> "FE":
+        modulus = self.MOD
+        r = modulus
+        new_r = self.value
+        if new_r < 0:
+            new_r += modulus
+        _, _, t = extended_euclidean(r, new_r)
+        t = _trunc_rem(t, modulus)
+        if t < 0:
+            t += modulus
+        return type(self)(t)
+
+    def div_ref(self, o: "FE") -> "FE":
+        return self.mul_ref(o.inverse())
+
+    def sanitize(self) -> "FE":
+        v = _trunc_rem(self.value, self.MOD)
+        if v < 0:
+            v += self.MOD
+        out = type(self).__new__(type(self))
+        out.value = v
+        return out
+
+    # operators (field.rs:290-387)
+    def __eq__(self, o) -> bool:  # field.rs:290-294: equality on sanitized values
+        return isinstance(o, FE) and self.MOD == o.MOD and self.sanitize().value == o.sanitize().value
+
+    def __hash__(self):
+        return hash((self.MOD, self.sanitize().value))
+
+    def __add__(self, o):
+        return self.add_ref(o)
+
+    def __sub__(self, o):
+        return self.sub_ref(o)
+
+    def __mul__(self, o):
+        return self.mul_ref(o)
+
+    def __neg__(self):  # field.rs:373-379
+        return type(self)(0) - self
+
+    def __truediv__(self, o):
+        return self.div_ref(o)
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.value})"
+
+
+class Fq(FE):  # bn128.rs:29 (base field, BN128Modulus)
+    __slots__ = ()
+    MOD = P_MOD
+
+
+class Fr(FE):  # bn128.rs:30 FqOrder = FiniteFieldElement<ModEIP197>
+    __slots__ = ()
+    MOD = R_MOD
+
+
+FqOrder = Fr
+
+
+def make_field(modulus: int, name: str = "Fm"):
+    """define_myzkp_modulus_type! (field.rs:408-425) for the small-modulus KATs."""
+    return type(name, (FE,), {"MOD": modulus, "__slots__": ()})
+
+
+class G1Point:
+    """EllipticCurvePoint<Fq, BN128Curve> (curve/curve.rs:17-46): affine,
+    infinity = (None, None), no on-curve check (curve.rs:26-28)."""
+
+    __slots__ = ("x", "y")
+
+    def __init__(self, x: Optional[Fq], y: Optional[Fq]):
+        self.x = x
+        self.y = y
+
+    @staticmethod
+    def new(x: Fq, y: Fq) -> "G1Point":
+        return G1Point(x, y)
+
+    @staticmethod
+    def point_at_infinity() -> "G1Point":
+        return G1Point(None, None)
+
+    def is_point_at_infinity(self) -> bool:
+        return self.x is None or self.y is None
+
+    def clone(self) -> "G1Point":
+        return G1Point(self.x, self.y)
+
+    def line_slope(self, other: "G1Point") -> Fq:
+        """curve.rs:56-70."""
+        a = Fq.from_value(CURVE_A)
+        x1, y1, x2, y2 = self.x, self.y, other.x, other.y
+        if self.x == other.x:
+            return (x1.mul_ref(x1) * Fq.from_value(3) + a) / (y1.mul_ref(Fq.from_value(2)))
+        return y2.sub_ref(y1) / x2.sub_ref(x1)
+
+    def double(self) -> "G1Point":
+        """curve.rs:72-85."""
+        if self.is_point_at_infinity():
+            return self.clone()
+        slope = self.line_slope(self)
+        x, y = self.x, self.y
+        new_x = slope.mul_ref(slope).sub_ref(x).sub_ref(x)
+        new_y = -slope.mul_ref(new_x) + slope * x - y
+        return G1Point(new_x, new_y)
+
+    def inplace_double(self) -> None:
+        """curve.rs:87-101."""
+        d = self.double()
+        self.x, self.y = d.x, d.y
+
+    def add_ref(self, other: "G1Point") -> "G1Point":
+        """curve.rs:103-128."""
+        if self.is_point_at_infinity():
+            return other.clone()
+        if other.is_point_at_infinity():
+            return self.clone()
+        if self.x == other.x and self.y == other.y:
+            return self.double()
+        elif self.x == other.x:
+            return G1Point.point_at_infinity()
+        slope = self.line_slope(other)
+        x1, y1, x2 = self.x, self.y, other.x
+        new_x = slope.mul_ref(slope).sub_ref(x1).sub_ref(x2)
+        new_y = (-slope).mul_ref(new_x) + slope.mul_ref(x1).sub_ref(y1)
+        return G1Point(new_x, new_y)
+
+    def add_assign_ref(self, other: "G1Point") -> None:
+        """curve.rs:130-161."""
+        s = self.add_ref(other)
+        self.x, self.y = s.x, s.y
+
+    def mul_ref(self, scalar: int) -> "G1Point":
+        """curve.rs:163-191: LSB-first double-and-add; 0 -> infinity; negative panics."""
+        if scalar == 0:
+            return G1Point.point_at_infinity()
+        if scalar < 0:
+            raise ValueError("multiplier should be non-negative")  # curve.rs:174-176
+        result = G1Point.point_at_infinity()
+        current = self.clone()
+        bits = scalar
+        while bits != 0:
+            if bits & 1:
+                result.add_assign_ref(current)
+            current.inplace_double()
+            bits >>= 1
+        return result
+
+    def __neg__(self):  # curve.rs:216-225
+        if self.is_point_at_infinity():
+            return self
+        return G1Point(self.x, -self.y)
+
+    def __add__(self, o):
+        return self.add_ref(o)
+
+    def __sub__(self, o):
+        return self + (-o)
+
+    def __mul__(self, k: int):
+        return self.mul_ref(k)
+
+    def __eq__(self, o) -> bool:
+        if not isinstance(o, G1Point):
+            return False
+        if self.is_point_at_infinity() or o.is_point_at_infinity():
+            return self.is_point_at_infinity() and o.is_point_at_infinity()
+        return self.x == o.x and self.y == o.y
+
+    def affine_ints(self) -> Optional[Tuple[int, int]]:
+        """Canonical (x mod p, y mod p) or None for infinity."""
+        if self.is_point_at_infinity():
+            return None
+        return self.x.sanitize().value, self.y.sanitize().value
+
+    def __repr__(self):
+        return f"G1Point({self.affine_ints()})"
+
+
+def generator_g1() -> G1Point:
+    """bn128.rs:185-188."""
+    return G1Point.new(Fq.from_value(1), Fq.from_value(2))
+
+
+def order() -> int:
+    """bn128.rs:207-212."""
+    return R_MOD
+
+
+class Polynomial:
+    """Polynomial<F> (polynomial.rs:69-74): coefficients low -> high degree."""
+
+    def __init__(self, coef: Sequence[FE], field=Fr):
+        self.coef: List[FE] = list(coef)
+        self.F = field if not self.coef else type(self.coef[0])
+
+    @staticmethod
+    def trim_trailing_zeros(coef: Sequence[FE]) -> List[FE]:
+        """polynomial.rs:85-91 (the slice copy is the reference's O(d^2) source)."""
+        end = 0
+        for pos in range(len(coef) - 1, -1, -1):
+            if coef[pos].sanitize().value != 0:
+                end = pos + 1
+                break
+        return list(coef[:end])
+
+    def degree(self) -> int:
+        t = self.trim_trailing_zeros(self.coef)
+        return len(t) - 1 if t else -1
+
+    def is_zero(self) -> bool:
+        return self.degree() == -1
+
+    def eval(self, point: FE) -> FE:
+        """polynomial.rs:120-128: running-power sum."""
+        F = self.F
+        result = F.zero()
+        tp = F.one()
+        for c in self.coef:
+            result = result + tp.mul_ref(c)
+            tp = tp.mul_ref(point)
+        return result
+
+    def eval_with_powers_on_curve(self, powers: Sequence[G1Point]) -> G1Point:
+        """polynomial.rs:156-165: the naive MSM (index panics if too few powers)."""
+        result = G1Point.point_at_infinity()
+        for i, c in enumerate(self.coef):
+            result.add_assign_ref(powers[i].mul_ref(c.sanitize().get_value()))
+        return result
+
+    @staticmethod
+    def from_monomials(x_values: Sequence[FE], field=Fr) -> "Polynomial":
+        """polynomial.rs:202-212."""
+        F = type(x_values[0]) if x_values else field
+        poly = Polynomial([F.one()], F)
+        for x in x_values:
+            poly = poly.mul_ref(Polynomial([F.zero() - x, F.one()], F))
+        return poly
+
+    def add_ref(self, other: "Polynomial") -> "Polynomial":
+        """polynomial.rs:214-228."""
+        F = self.F
+        n = max(len(self.coef), len(other.coef))
+        zero = F.zero()
+        out = []
+        for i in range(n):
+            a = self.coef[i] if i < len(self.coef) else zero
+            b = other.coef[i] if i < len(other.coef) else zero
+            out.append(a.add_ref(b))
+        return Polynomial(self.trim_trailing_zeros(out), F)
+
+    def __neg__(self):  # polynomial.rs:465-473
+        return Polynomial([-c for c in self.coef], self.F)
+
+    def __sub__(self, other):  # polynomial.rs:517-523
+        return self.add_ref(-other)
+
+    def __add__(self, other):
+        return self.add_ref(other)
+
+    def mul_ref(self, other: "Polynomial") -> "Polynomial":
+        """polynomial.rs:302-316."""
+        F = self.F
+        if self.is_zero() or other.is_zero():
+            return Polynomial([], F)
+        result = [F.zero() for _ in range(self.degree() + other.degree() + 1)]
+        for i, a in enumerate(self.coef):
+            for j, b in enumerate(other.coef):
+                result[i + j] = result[i + j].add_ref(a.mul_ref(b))
+        return Polynomial(self.trim_trailing_zeros(result), F)
+
+    def scalar_mul(self, s: FE) -> "Polynomial":  # polynomial.rs:553-561
+        return Polynomial([c.mul_ref(s) for c in self.coef], self.F)
+
+    def div_rem_ref(self, other: "Polynomial") -> Tuple["Polynomial", "Polynomial"]:
+        """polynomial.rs:371-405: schoolbook long division (trim per iteration)."""
+        F = self.F
+        if self.degree() < other.degree():
+            return Polynomial([], F), Polynomial(self.coef, F)
+        remainder = self.trim_trailing_zeros(self.coef)
+        divisor = self.trim_trailing_zeros(other.coef)
+        if len(divisor) == 0:
+            return Polynomial([], F), Polynomial(self.coef, F)
+        lead_inv = divisor[-1].inverse()
+        quotient = [F.zero() for _ in range(self.degree() - other.degree() + 1)]
+        while len(remainder) >= len(divisor):
+            lead_term = remainder[-1].mul_ref(lead_inv)
+            deg_diff = len(remainder) - len(divisor)
+            quotient[deg_diff] = lead_term
+            for i in range(len(divisor)):
+                remainder[deg_diff + i] = remainder[deg_diff + i].sub_ref(lead_term.mul_ref(divisor[i]))
+            remainder = self.trim_trailing_zeros(remainder)
+        return Polynomial(self.trim_trailing_zeros(quotient), F), Polynomial(remainder, F)
+
+    def __truediv__(self, other):  # polynomial.rs:583-597
+        return self.div_rem_ref(other)[0]
+
+    def canonical(self) -> List[int]:
+        return [c.sanitize().value for c in self.coef]
+
+
+# --- kzg.rs -----------------------------------------------------------------
+class PublicKeyKZG:
+    """kzg.rs:8-11 (powers_2 / G2 is verifier-side and out of scope)."""
+
+    def __init__(self, powers_1: List[G1Point]):
+        self.powers_1 = powers_1
+
+
+class ProofKZG:
+    """kzg.rs:15-18."""
+
+    def __init__(self, y: Fr, w: G1Point):
+        self.y = y
+        self.w = w
+
+
+def setup_kzg(g1: G1Point, max_d: int, alpha: int) -> PublicKeyKZG:
+    """kzg.rs:27-40 with the unseeded alpha (field.rs:198-206) injected:
+    max_d + 1 points [alpha^i]G (kzg.rs:32)."""
+    a = Fr.from_value(alpha)
+    powers_1 = []
+    alpha_power = Fr.one()
+    for _ in range(1 + max_d):
+        powers_1.append(g1.mul_ref(alpha_power.get_value()))
+        alpha_power = alpha_power * a
+    return PublicKeyKZG(powers_1)
+
+
+def commit_kzg(f: Polynomial, pk: PublicKeyKZG) -> G1Point:
+    """kzg.rs:57-59."""
+    return f.eval_with_powers_on_curve(pk.powers_1)
+
+
+def open_kzg(f: Polynomial, u: Fr, pk: PublicKeyKZG) -> ProofKZG:
+    """kzg.rs:61-72."""
+    y = f.eval(u)
+    y_poly = Polynomial([y], Fr)
+    f_u = (f - y_poly) / Polynomial.from_monomials([u])
+    return ProofKZG(y, f_u.eval_with_powers_on_curve(pk.powers_1))
+
+
+# --- gemini.rs --------------------------------------------------------------
+class SplitFoldError(ValueError):
+    """gemini.rs:15-32."""
+
+
+def split_and_fold(coef: Sequence[FE], rhos: Sequence[FE]) -> List[Polynomial]:
+    """gemini.rs:51-103: log2(n)+1 polynomials incl. the original."""
+    n = len(coef)
+    if bin(n).count("1") != 1:
+        raise SplitFoldError(f"coefs.len() must be a power of two, but got {n}")
+    log2_n = n.bit_length() - 1
+    if len(rhos) != log2_n:
+        raise SplitFoldError(f"points.len() must be {log2_n}, but got {len(rhos)}")
+    F = type(coef[0])
+    f = Polynomial(list(coef), F)
+    fs = [Polynomial(list(coef), F)]
+    for i in range(1, log2_n + 1):
+        f_e = Polynomial([x if k % 2 == 0 else F.zero() for k, x in enumerate(f.coef)], F)
+        f_o = Polynomial([x if k % 2 == 0 else F.zero() for k, x in enumerate(f.coef[1:])], F)
+        f_i = f_e + f_o.scalar_mul(rhos[i - 1])
+        # gemini.rs:88-96 keeps the even positions of f_i.  f_i has been trimmed
+        # by add_ref, so a fold with trailing zero coefficients comes out short;
+        # for the commitment that is immaterial.
+        f = Polynomial([x for k, x in enumerate(f_i.coef) if k % 2 == 0], F)
+        fs.append(Polynomial(list(f.coef), F))
+    return fs
+
+
+def commit_gemini(polys: Sequence[Polynomial], pk: PublicKeyKZG) -> List[G1Point]:
+    """gemini.rs:112-114."""
+    return [commit_kzg(p, pk) for p in polys]
+
+
+# --- O(N) algebraic expected values for sizes the naive path cannot reach ---
+def _pinv(v: int, m: int) -> int:
+    return pow(v, -1, m)
+
+
+def _fast_add(p1, p2):
+    """Affine add on plain ints (None = infinity); same law as curve.rs:103-128,
+    using pow(.,-1,p) instead of ext-Euclid.  Used only for expected values."""
+    if p1 is None:
+        return p2
+    if p2 is None:
+        return p1
+    x1, y1 = p1
+    x2, y2 = p2
+    if x1 == x2:
+        if y1 != y2 or y1 == 0:
+            return None
+        s = 3 * x1 * x1 * _pinv(2 * y1, P_MOD) % P_MOD
+    else:
+        s = (y2 - y1) * _pinv(x2 - x1, P_MOD) % P_MOD
+    x3 = (s * s - x1 - x2) % P_MOD
+    return x3, (s * (x1 - x3) - y1) % P_MOD
+
+
+def fast_mul(k: int, pt=(1, 2)):
+    """[k]P on plain ints (MSB-first); validated against G1Point.mul_ref in tests."""
+    k %= R_MOD
+    acc = None
+    for bit in bin(k)[2:] if k else "":
+        acc = _fast_add(acc, acc)
+        if bit == "1":
+            acc = _fast_add(acc, pt)
+    return acc
+
+
+def expected_commit(coefs: Sequence[int], alpha: int):
+    """C = [f(alpha) mod r]G for SRS [alpha^i]G (SURVEY 8c large-N oracle)."""
+    acc = 0
+    for c in reversed(coefs):
+        acc = (acc * alpha + c) % R_MOD
+    return fast_mul(acc)
+
+
+def synthetic_division(coefs: Sequence[int], u: int) -> Tuple[int, List[int]]:
+    """y = f(u) and q = (f - y)/(x - u), canonical ints; equals polynomial.rs:371-405
+    for the monic linear divisor (checked against div_rem_ref in tests)."""
+    n = len(coefs)
+    if n == 0:
+        return 0, []
+    q = [0] * (n - 1)
+    c = 0
+    for i in range(n - 1, 0, -1):
+        c = (coefs[i] + u * c) % R_MOD
+        q[i - 1] = c
+    y = (coefs[0] + u * c) % R_MOD
+    return y, q
+
+
+def expected_open(coefs: Sequence[int], u: int, alpha: int):
+    """(y, W) with W = [(f(alpha) - y)/(alpha - u)]G, valid for alpha != u."""
+    y, _ = synthetic_division(coefs, u)
+    fa = 0
+    for c in reversed(coefs):
+        fa = (fa * alpha + c) % R_MOD
+    k = (fa - y) * _pinv((alpha - u) % R_MOD, R_MOD) % R_MOD
+    return y, fast_mul(k)
+
+
+def fold_ints(coefs: Sequence[int], rhos: Sequence[int]) -> List[List[int]]:
+    """Canonical-int form of split_and_fold (no trimming)."""
+    out = [list(c % R_MOD for c in coefs)]
+    cur = out[0]
+    for rho in rhos:
+        cur = [(cur[2 * k] + rho * cur[2 * k + 1]) % R_MOD for k in range(len(cur) // 2)]
+        out.append(cur)
+    return out
+
+
+# --- wire encodings (examples/sumcheck/src/utils.rs:51-72) --------
+def fe_to_bytes(v: int) -> bytes:
+    return int(v).to_bytes(32, "little")
+
+
+def fe_from_bytes(b: bytes) -> int:
+    return int.from_bytes(b, "little")
+
+
+def point_to_bytes(pt) -> bytes:
+    """affine (x, y) ints or None -> 64 B (infinity = 64 zero bytes)."""
+    if pt is None:
+        return bytes(64)
+    return fe_to_bytes(pt[0]) + fe_to_bytes(pt[1])
+
+
+def point_from_bytes(b: bytes):
+    if b == bytes(64):
+        return None
+    return fe_from_bytes(b[:32]), fe_from_bytes(b[32:64])

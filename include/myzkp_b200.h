@@ -1,0 +1,131 @@
+/* myzkp_b200 - C ABI of the B200-native KZG prover hot path (BN128).
+ *
+ * Drop-in boundary for MyZKP's `setup_kzg` / `commit_kzg` / `open_kzg` /
+ * `commit_gemini` (reference: myzkp/src/modules/algebra/kzg.rs:27-72,
+ * gemini.rs:51-114).  The reference has no FFI for this path (they are plain
+ * generic Rust calls); its only host<->device convention is
+ * myzkp/examples/sumcheck/src/utils.rs:51-72 (field element = 32 bytes,
+ * little-endian, canonical, non-Montgomery), which this ABI keeps.
+ *
+ * Encodings
+ *   Fr / Fq element : 32 B little-endian, canonical (< modulus), non-Montgomery.
+ *   G1 point        : x || y (64 B); the point at infinity is 64 zero bytes
+ *                     (reference: EllipticCurvePoint{x:None,y:None}, curve.rs:17-46).
+ * Ownership: the caller owns every host buffer; the ctx owns all device memory.
+ * Errors: 0 = ok, negative = error (message via myzkp_last_error); never aborts.
+ * Threading: one in-flight call per ctx.
+ * There is NO CPU fallback: every entry point runs CUDA kernels on the ctx's
+ * device and fails with MYZKP_ERR_CUDA when no device is usable.
+ */
+#ifndef MYZKP_B200_H
+#define MYZKP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct myzkp_ctx myzkp_ctx;
+
+enum {
+  MYZKP_OK = 0,
+  MYZKP_ERR_INVALID_ARG = -1,  /* null pointer; n > srs_len (reference panics: polynomial.rs:162);
+                                  gemini length not a power of two (gemini.rs:55-57) */
+  MYZKP_ERR_NONCANONICAL = -2, /* an input limb vector >= modulus */
+  MYZKP_ERR_CUDA = -3,
+  MYZKP_ERR_OOM = -4,
+  MYZKP_ERR_NO_SRS = -5
+};
+
+/* ---- context ---------------------------------------------------------- */
+int myzkp_ctx_create(myzkp_ctx** out, int device_id);
+int myzkp_ctx_destroy(myzkp_ctx* ctx);
+/* Run all work of this ctx on an existing CUDA stream (cudaStream_t). */
+int myzkp_ctx_set_stream(myzkp_ctx* ctx, void* cuda_stream);
+int myzkp_ctx_sync(myzkp_ctx* ctx);
+const char* myzkp_last_error(const myzkp_ctx* ctx);
+/* Number of this library's kernels launched by the ctx so far. */
+uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
+/* MSM tuning knobs (0 = automatic): window bits c in {8,16,24}; entries per
+ * accumulate segment. */
+int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
+
+/* pinned host memory for callers that want DMA-able buffers */
+int myzkp_host_alloc(void** out, size_t bytes);
+int myzkp_host_free(void* p);
+
+/* ---- SRS = PublicKeyKZG.powers_1 (kzg.rs:8-11, 27-40) ------------------- */
+/* Load n affine points.  Builds the resident table of 2^(8j) multiples. */
+int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le /* n*64 */, size_t n);
+/* setup_kzg with the (unseeded, kzg.rs:28) alpha injected: points
+ * [alpha^(first+i)]G for i < n; n = max_d + 1 (kzg.rs:32).  `first` lets a
+ * rank generate only its shard of a range-sharded SRS. */
+int myzkp_srs_generate_g1(myzkp_ctx* ctx, const uint8_t alpha_le[32], size_t first, size_t n);
+int myzkp_srs_read_g1(myzkp_ctx* ctx, size_t off, size_t n, uint8_t* out /* n*64 */);
+size_t myzkp_srs_len(const myzkp_ctx* ctx);
+
+/* ---- commit / open, host buffers --------------------------------------- */
+/* commit_kzg (kzg.rs:57-59) = Polynomial::eval_with_powers_on_curve
+ * (polynomial.rs:156-165): C = sum_i coef_i * powers_1[i].  n == 0 -> infinity. */
+int myzkp_kzg_commit(myzkp_ctx* ctx, const uint8_t* coefs_le /* n*32 */, size_t n, uint8_t out_c[64]);
+/* open_kzg (kzg.rs:61-72): y = f(u) (polynomial.rs:120-128),
+ * q = (f - y)/(x - u) (polynomial.rs:371-405), W = commit(q).
+ * n <= 1 -> W = infinity, y = f_0 (or 0) (polynomial.rs:372-374). */
+int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32],
+                   uint8_t out_y[32], uint8_t out_w[64]);
+/* commit_gemini (gemini.rs:112-114) over k polynomials. */
+int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const size_t* ns, size_t k,
+                           uint8_t* out /* k*64 */);
+/* split_and_fold (gemini.rs:51-103) + commit_gemini: n_pow2 = 2^m coefficients,
+ * m challenges; writes m+1 commitments (original first).  If out_folds is not
+ * NULL it receives the m folded polynomials back to back (2^(m-1) + ... + 1
+ * coefficients, 32 B each). */
+int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_pow2,
+                             const uint8_t* rhos_le /* m*32 */, uint8_t* out /* (m+1)*64 */,
+                             uint8_t* out_folds /* (n_pow2-1)*32 or NULL */);
+/* Polynomial::eval (polynomial.rs:120-128). */
+int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]);
+/* y and the quotient coefficients themselves (n-1 of them; n >= 1). */
+int myzkp_fr_quotient(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32],
+                      uint8_t out_y[32], uint8_t* out_q /* (n-1)*32 */);
+
+/* ---- device-pointer variants (inputs/outputs already in HBM) ------------ */
+/* Asynchronous on the ctx stream.  d_out_* must be device memory. */
+int myzkp_kzg_commit_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, void* d_out_c64);
+int myzkp_kzg_open_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
+                       void* d_out_y32, void* d_out_w64);
+/* Partial MSM against the resident SRS points [srs_off, srs_off+n): leaves a
+ * 128-byte XYZZ group element (internal Montgomery form) in d_out_xyzz128.
+ * Used by the range-sharded multi-GPU commit: one partial per rank, exchanged
+ * over NCCL and summed with myzkp_g1_sum_partials_dev. */
+int myzkp_g1_msm_partial_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n, size_t srs_off,
+                             void* d_out_xyzz128);
+/* Sum k XYZZ partials (k*128 B, device) -> canonical affine 64 B (device). */
+int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64);
+/* Sharded open: per-rank pieces of the quotient scan over a contiguous
+ * coefficient range f[lo, lo+n).  eval gives (h, u^n) with h = sum f_{lo+i} u^i.
+ * quotient takes the carry c_n entering from above (the combined h of all
+ * higher ranges) and, with c_i = f_{lo+i} + u c_{i+1}, writes
+ * d_q[i] = c_{i+1} = q_{lo+i} (the quotient coefficient that pairs with SRS
+ * point lo+i) and *d_c0 = c_0 (y when lo == 0; the carry for the range below
+ * otherwise). */
+int myzkp_fr_range_eval_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
+                            void* d_out_h32, void* d_out_upow32);
+int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
+                                const uint8_t carry_in_le[32], void* d_q /* n*32 */, void* d_c0 /* 32 */);
+
+/* ---- test hooks: batched field / group ops for parity tests -------------
+ * op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 neg(a);  field: 0 = Fq, 1 = Fr.
+ * Inputs/outputs canonical 32 B LE, host pointers. */
+int myzkp_test_field_op(myzkp_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
+                        uint8_t* out, size_t n);
+/* op: 0 a[i]+b[i] (mixed add), 1 double(a[i]), 2 [k]a[i] with k = the 256-bit
+ * integer in the first 32 bytes of b[i] (double-and-add in XYZZ), 3 a[i]+b[i]
+ * through XYZZ+XYZZ with non-trivial denominators.  Points are 64 B affine. */
+int myzkp_test_g1_op(myzkp_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYZKP_B200_H */

@@ -1,0 +1,11 @@
+"""myzkp_b200: B200-native KZG prover hot path (BN128) behind MyZKP's own
+setup_kzg / commit_kzg / open_kzg / commit_gemini surface.
+
+The work is done by libmyzkp_b200.so (hand-written CUDA for sm_100a, C ABI in
+include/myzkp_b200.h).  There is no CPU fallback.
+"""
+from .context import Context, R_MOD, P_MOD  # noqa: F401
+from .kzg import (  # noqa: F401
+    BN128, CommitmentKZG, G1Point, Polynomial, ProofKZG, PublicKeyKZG, commit_kzg, open_kzg, setup_kzg,
+)
+from .gemini import SplitFoldError, commit_gemini, split_and_fold_commit  # noqa: F401

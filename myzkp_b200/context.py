@@ -1,0 +1,210 @@
+"""Device context: owns the stream, the resident SRS table and all scratch."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+
+
+def scalars_to_bytes(values) -> np.ndarray:
+    """ints (or an (n,32) uint8 / (n,4) uint64 / (n,8) uint32 array) -> contiguous (n,32) uint8, LE."""
+    if isinstance(values, np.ndarray):
+        a = np.ascontiguousarray(values)
+        if a.dtype == np.uint8 and a.ndim == 2 and a.shape[1] == 32:
+            return a
+        if a.dtype == np.uint64 and a.ndim == 2 and a.shape[1] == 4:
+            return a.view(np.uint8).reshape(-1, 32)
+        if a.dtype == np.uint32 and a.ndim == 2 and a.shape[1] == 8:
+            return a.view(np.uint8).reshape(-1, 32)
+        raise TypeError(f"unsupported scalar array {a.dtype} {a.shape}")
+    buf = b"".join(int(v).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint8).reshape(-1, 32).copy() if buf else np.zeros((0, 32), np.uint8)
+
+
+def bytes_to_int(b) -> int:
+    return int.from_bytes(bytes(b), "little")
+
+
+def point_from_bytes(b) -> Optional[tuple]:
+    b = bytes(b)
+    if b == bytes(64):
+        return None
+    return int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little")
+
+
+def point_to_bytes(pt) -> bytes:
+    if pt is None:
+        return bytes(64)
+    return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One per GPU (one process per GPU in multi-GPU runs)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        code = self._lib.myzkp_ctx_create(ctypes.byref(h), int(device))
+        if code != 0:
+            raise _lib.MyzkpError(code, f"cannot create a CUDA context on device {device} (no CPU fallback exists)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.myzkp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, code):
+        _lib.check(self.h, code)
+
+    # -- plumbing
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.myzkp_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(self._lib.myzkp_ctx_sync(self.h))
+
+    def set_msm_params(self, window_bits: int = 0, segment_len: int = 0):
+        self._ck(self._lib.myzkp_ctx_set_msm_params(self.h, window_bits, segment_len))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.myzkp_kernel_launches(self.h))
+
+    # -- SRS
+    def srs_generate(self, alpha: int, n: int, first: int = 0):
+        a = np.frombuffer(int(alpha % R_MOD).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_srs_generate_g1(self.h, _ptr(a), first, n))
+
+    def srs_load(self, points: Sequence):
+        """points: list of (x, y) / None, or an (n,64) uint8 array."""
+        if isinstance(points, np.ndarray):
+            a = np.ascontiguousarray(points, dtype=np.uint8).reshape(-1, 64)
+        else:
+            a = np.frombuffer(b"".join(point_to_bytes(p) for p in points), dtype=np.uint8).reshape(-1, 64).copy()
+        self._ck(self._lib.myzkp_srs_load_g1(self.h, _ptr(a), a.shape[0]))
+
+    def srs_read(self, off: int, n: int):
+        out = np.zeros((n, 64), np.uint8)
+        self._ck(self._lib.myzkp_srs_read_g1(self.h, off, n, _ptr(out)))
+        return [point_from_bytes(out[i]) for i in range(n)]
+
+    @property
+    def srs_len(self) -> int:
+        return int(self._lib.myzkp_srs_len(self.h))
+
+    # -- commit / open on host buffers
+    def commit(self, coefs):
+        a = scalars_to_bytes(coefs)
+        out = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_kzg_commit(self.h, _ptr(a), a.shape[0], _ptr(out)))
+        return point_from_bytes(out)
+
+    def open(self, coefs, u: int):
+        a = scalars_to_bytes(coefs)
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        y = np.zeros(32, np.uint8)
+        w = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_kzg_open(self.h, _ptr(a), a.shape[0], _ptr(ub), _ptr(y), _ptr(w)))
+        return bytes_to_int(y), point_from_bytes(w)
+
+    def fr_eval(self, coefs, u: int) -> int:
+        a = scalars_to_bytes(coefs)
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        y = np.zeros(32, np.uint8)
+        self._ck(self._lib.myzkp_fr_eval(self.h, _ptr(a), a.shape[0], _ptr(ub), _ptr(y)))
+        return bytes_to_int(y)
+
+    def fr_quotient(self, coefs, u: int):
+        a = scalars_to_bytes(coefs)
+        n = a.shape[0]
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        y = np.zeros(32, np.uint8)
+        q = np.zeros((max(n - 1, 0), 32), np.uint8)
+        self._ck(self._lib.myzkp_fr_quotient(self.h, _ptr(a), n, _ptr(ub), _ptr(y), _ptr(q)))
+        return bytes_to_int(y), q
+
+    def gemini_fold_commit(self, coefs, rhos, want_folds: bool = False):
+        a = scalars_to_bytes(coefs)
+        n = a.shape[0]
+        r = scalars_to_bytes(rhos)
+        m = r.shape[0]
+        out = np.zeros((m + 1, 64), np.uint8)
+        folds = np.zeros((max(n - 1, 0), 32), np.uint8) if want_folds else None
+        self._ck(
+            self._lib.myzkp_gemini_fold_commit(
+                self.h, _ptr(a), n, _ptr(r) if m else None, _ptr(out), _ptr(folds) if want_folds and n > 1 else None
+            )
+        )
+        pts = [point_from_bytes(out[i]) for i in range(m + 1)]
+        return (pts, folds) if want_folds else pts
+
+    # -- test hooks
+    def test_field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        aa = scalars_to_bytes(a)
+        bb = scalars_to_bytes(b) if b is not None else None
+        out = np.zeros_like(aa)
+        self._ck(self._lib.myzkp_test_field_op(self.h, field, op, _ptr(aa), _ptr(bb) if bb is not None else None, _ptr(out), aa.shape[0]))
+        return out
+
+    def test_g1_op(self, op: int, a, b=None):
+        aa = np.frombuffer(b"".join(point_to_bytes(p) for p in a), dtype=np.uint8).reshape(-1, 64).copy()
+        bb = None
+        if b is not None:
+            bb = np.frombuffer(b"".join(x if isinstance(x, (bytes, bytearray)) else point_to_bytes(x) for x in b), dtype=np.uint8).reshape(-1, 64).copy()
+        out = np.zeros_like(aa)
+        self._ck(self._lib.myzkp_test_g1_op(self.h, op, _ptr(aa), _ptr(bb) if bb is not None else None, _ptr(out), aa.shape[0]))
+        return [point_from_bytes(out[i]) for i in range(aa.shape[0])]
+
+
+# -- device-pointer entry points (used by bench.py and the multi-GPU layer) ----
+def _dev_methods():
+    def commit_dev(self, d_coefs: int, n: int, d_out64: int):
+        """Asynchronous on the ctx stream; pointers are raw device addresses (e.g. tensor.data_ptr())."""
+        self._ck(self._lib.myzkp_kzg_commit_dev(self.h, ctypes.c_void_p(d_coefs), n, ctypes.c_void_p(d_out64)))
+
+    def open_dev(self, d_coefs: int, n: int, u: int, d_out_y32: int, d_out_w64: int):
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_kzg_open_dev(self.h, ctypes.c_void_p(d_coefs), n, _ptr(ub), ctypes.c_void_p(d_out_y32),
+                                              ctypes.c_void_p(d_out_w64)))
+
+    def msm_partial_dev(self, d_scalars: int, n: int, srs_off: int, d_out_xyzz128: int):
+        self._ck(self._lib.myzkp_g1_msm_partial_dev(self.h, ctypes.c_void_p(d_scalars), n, srs_off,
+                                                    ctypes.c_void_p(d_out_xyzz128)))
+
+    def sum_partials_dev(self, d_partials: int, k: int, d_out64: int):
+        self._ck(self._lib.myzkp_g1_sum_partials_dev(self.h, ctypes.c_void_p(d_partials), k, ctypes.c_void_p(d_out64)))
+
+    def fr_range_eval_dev(self, d_coefs: int, n: int, u: int, d_out_h32: int, d_out_upow32: int):
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_fr_range_eval_dev(self.h, ctypes.c_void_p(d_coefs), n, _ptr(ub),
+                                                   ctypes.c_void_p(d_out_h32), ctypes.c_void_p(d_out_upow32)))
+
+    def fr_range_quotient_dev(self, d_coefs: int, n: int, u: int, carry_in: int, d_q: int, d_c0: int):
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        cb = np.frombuffer(int(carry_in).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_fr_range_quotient_dev(self.h, ctypes.c_void_p(d_coefs), n, _ptr(ub), _ptr(cb),
+                                                       ctypes.c_void_p(d_q), ctypes.c_void_p(d_c0)))
+
+    for f in (commit_dev, open_dev, msm_partial_dev, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev):
+        setattr(Context, f.__name__, f)
+
+
+_dev_methods()

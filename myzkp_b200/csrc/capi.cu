@@ -1,0 +1,301 @@
+// extern "C" entry points of libmyzkp_b200.so (see include/myzkp_b200.h).
+#include <string.h>
+
+#include <vector>
+
+#include "ctx.cuh"
+
+using namespace mz;
+
+namespace {
+
+// canonical little-endian moduli for host-side checks of the 32-byte scalars
+const uint8_t kRModLE[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                             0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+bool fr_bytes_canonical(const uint8_t* b) {
+  for (int i = 31; i >= 0; i--) {
+    if (b[i] < kRModLE[i]) return true;
+    if (b[i] > kRModLE[i]) return false;
+  }
+  return false;
+}
+
+// layout of ctx->small (4 KiB)
+constexpr size_t kSmallFlag = 512;    // int: non-canonical input seen
+constexpr size_t kSmallY = 640;       // 32 B: y / c0
+constexpr size_t kSmallXyzz = 1024;   // XYZZ result(s): up to 16 slots (2 KiB)
+constexpr size_t kSmallPoint = 3072;  // 64 B affine bytes result
+
+int begin_call(myzkp_ctx* ctx) {
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+  MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->small.as<uint8_t>() + kSmallFlag, 0, sizeof(int), ctx->stream));
+  return MYZKP_OK;
+}
+
+int end_call_check_flag(myzkp_ctx* ctx) {
+  int h_flag = 0;
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, ctx->small.as<uint8_t>() + kSmallFlag, sizeof(int), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_flag) return fail(ctx, MYZKP_ERR_NONCANONICAL, "input scalar >= r (callers must sanitize, field.rs:260-270)");
+  return MYZKP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int myzkp_ctx_create(myzkp_ctx** out, int device_id) {
+  if (!out) return MYZKP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device_id < 0 || device_id >= count) return MYZKP_ERR_CUDA;
+  if (cudaSetDevice(device_id) != cudaSuccess) return MYZKP_ERR_CUDA;
+  myzkp_ctx* ctx = new myzkp_ctx();
+  ctx->device = device_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return MYZKP_ERR_CUDA;
+  }
+  ctx->own_stream = true;
+  *out = ctx;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_destroy(myzkp_ctx* ctx) {
+  if (!ctx) return MYZKP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->table) cudaFree(ctx->table);
+  if (ctx->gcomb) cudaFree(ctx->gcomb);
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->red_a, &ctx->red_b,
+                    &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_set_stream(myzkp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_sync(myzkp_ctx* ctx) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MYZKP_OK;
+}
+
+const char* myzkp_last_error(const myzkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  if (window_bits != 0 && window_bits != 8 && window_bits != 16 && window_bits != 24)
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window_bits must be 0, 8, 16 or 24");
+  if (segment_len < 0 || segment_len > 65536) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bad segment_len");
+  ctx->window_bits = window_bits;
+  ctx->segment_len = segment_len;
+  return MYZKP_OK;
+}
+
+int myzkp_host_alloc(void** out, size_t bytes) {
+  if (!out) return MYZKP_ERR_INVALID_ARG;
+  return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? MYZKP_OK : MYZKP_ERR_OOM;
+}
+int myzkp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MYZKP_OK : MYZKP_ERR_CUDA; }
+
+// ---- device-pointer variants ------------------------------------------------
+int myzkp_g1_msm_partial_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n, size_t srs_off, void* d_out_xyzz128) {
+  if (!ctx || (!d_scalars && n) || !d_out_xyzz128) return MYZKP_ERR_INVALID_ARG;
+  MZ_TRY(begin_call(ctx));
+  return msm_xyzz(ctx, static_cast<const uint32_t*>(d_scalars), n, srs_off, static_cast<XYZZ*>(d_out_xyzz128));
+}
+
+int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64) {
+  if (!ctx || (!d_partials && k) || !d_out_c64) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return sum_partials(ctx, static_cast<const XYZZ*>(d_partials), k, static_cast<uint8_t*>(d_out_c64));
+}
+
+int myzkp_kzg_commit_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, void* d_out_c64) {
+  if (!ctx || (!d_coefs && n) || !d_out_c64) return MYZKP_ERR_INVALID_ARG;
+  MZ_TRY(begin_call(ctx));
+  XYZZ* res = reinterpret_cast<XYZZ*>(ctx->small.as<uint8_t>() + kSmallXyzz);
+  MZ_TRY(msm_xyzz(ctx, static_cast<const uint32_t*>(d_coefs), n, 0, res));
+  return xyzz_to_bytes(ctx, res, 1, static_cast<uint8_t*>(d_out_c64));
+}
+
+int myzkp_kzg_open_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32], void* d_out_y32,
+                       void* d_out_w64) {
+  if (!ctx || (!d_coefs && n) || !u_le || !d_out_y32 || !d_out_w64) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  MZ_TRY(begin_call(ctx));
+  XYZZ* res = reinterpret_cast<XYZZ*>(ctx->small.as<uint8_t>() + kSmallXyzz);
+  if (n == 0) {
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(d_out_y32, 0, 32, ctx->stream));
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(d_out_w64, 0, 64, ctx->stream));
+    return MYZKP_OK;
+  }
+  MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
+  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag);
+  MZ_TRY(fr_check_canonical(ctx, static_cast<const uint32_t*>(d_coefs), n, flag));
+  MZ_TRY(fr_range_quotient(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, nullptr, ctx->scalars2.as<uint32_t>(),
+                           static_cast<uint32_t*>(d_out_y32)));
+  // q has n-1 coefficients (q[n-1] is the zero carry entering from above)
+  MZ_TRY(msm_xyzz(ctx, ctx->scalars2.as<uint32_t>(), n - 1, 0, res));
+  return xyzz_to_bytes(ctx, res, 1, static_cast<uint8_t*>(d_out_w64));
+}
+
+int myzkp_fr_range_eval_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32], void* d_out_h32,
+                            void* d_out_upow32) {
+  if (!ctx || (!d_coefs && n) || !u_le || !d_out_h32 || !d_out_upow32) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  MZ_TRY(begin_call(ctx));
+  return fr_range_eval(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, static_cast<uint32_t*>(d_out_h32),
+                       static_cast<uint32_t*>(d_out_upow32));
+}
+
+int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
+                                const uint8_t carry_in_le[32], void* d_q, void* d_c0) {
+  if (!ctx || (!d_coefs && n) || !u_le || !carry_in_le || (!d_q && n) || !d_c0) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le) || !fr_bytes_canonical(carry_in_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u or carry >= r");
+  MZ_TRY(begin_call(ctx));
+  if (n == 0) {
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_c0, carry_in_le, 32, cudaMemcpyHostToDevice, ctx->stream));
+    return MYZKP_OK;
+  }
+  return fr_range_quotient(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, carry_in_le,
+                           static_cast<uint32_t*>(d_q), static_cast<uint32_t*>(d_c0));
+}
+
+// ---- host-buffer variants ------------------------------------------------
+int myzkp_kzg_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, uint8_t out_c[64]) {
+  if (!ctx || (!coefs_le && n) || !out_c) return MYZKP_ERR_INVALID_ARG;
+  if (n > ctx->srs_n) return fail(ctx, n && !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG,
+                                  "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  if (n) {
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MZ_TRY(myzkp_kzg_commit_dev(ctx, ctx->scalars.p, n, s + kSmallPoint));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_c, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32],
+                   uint8_t out_w[64]) {
+  if (!ctx || (!coefs_le && n) || !u_le || !out_y || !out_w) return MYZKP_ERR_INVALID_ARG;
+  if (n > ctx->srs_n + 1 || (n > 1 && !ctx->table))
+    return fail(ctx, !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG, "quotient longer than the SRS");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  if (n) {
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MZ_TRY(myzkp_kzg_open_dev(ctx, ctx->scalars.p, n, u_le, s + kSmallY, s + kSmallPoint));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_w, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const size_t* ns, size_t k, uint8_t* out) {
+  if (!ctx || (k && (!coefs || !ns || !out))) return MYZKP_ERR_INVALID_ARG;
+  for (size_t i = 0; i < k; i++) MZ_TRY(myzkp_kzg_commit(ctx, coefs[i], ns[i], out + 64 * i));
+  return MYZKP_OK;
+}
+
+int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_pow2, const uint8_t* rhos_le,
+                             uint8_t* out, uint8_t* out_folds) {
+  if (!ctx || !coefs_le || !out) return MYZKP_ERR_INVALID_ARG;
+  if (n_pow2 == 0 || (n_pow2 & (n_pow2 - 1)))
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "coefs.len() must be a power of two (gemini.rs:55-57)");
+  int m = 0;
+  while (((size_t)1 << m) < n_pow2) m++;
+  if (m && !rhos_le) return MYZKP_ERR_INVALID_ARG;
+  if (n_pow2 > ctx->srs_n) return fail(ctx, !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS");
+  for (int i = 0; i < m; i++)
+    if (!fr_bytes_canonical(rhos_le + 32 * i)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "rho >= r");
+  MZ_TRY(begin_call(ctx));
+  // level buffers: all m+1 polynomials back to back (2n - 1 coefficients)
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure((2 * n_pow2) * 32 + (size_t)(m + 1) * 32));
+  uint32_t* base = ctx->scalars.as<uint32_t>();
+  uint32_t* d_rhos = base + (2 * n_pow2) * 8;
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(base, coefs_le, n_pow2 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (m) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_rhos, rhos_le, (size_t)m * 32, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((size_t)(m + 1) * sizeof(XYZZ) + (size_t)(m + 1) * 64));
+  XYZZ* res = ctx->xyzz_tmp.as<XYZZ>();
+  uint8_t* d_pts = reinterpret_cast<uint8_t*>(res + (m + 1));
+  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag);
+  MZ_TRY(fr_check_canonical(ctx, base, n_pow2, flag));
+  uint32_t* cur = base;
+  size_t len = n_pow2;
+  for (int lvl = 0; lvl <= m; lvl++) {
+    MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
+    if (lvl < m) {
+      uint32_t* nxt = cur + len * 8;
+      MZ_TRY(fr_fold(ctx, cur, len / 2, d_rhos + 8 * lvl, nxt));
+      cur = nxt;
+      len /= 2;
+    }
+  }
+  MZ_TRY(xyzz_to_bytes(ctx, res, (size_t)(m + 1), d_pts));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pts, (size_t)(m + 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_folds && n_pow2 > 1)
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_folds, base + n_pow2 * 8, (n_pow2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]) {
+  if (!ctx || (!coefs_le && n) || !u_le || !out_y) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  if (n) {
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MZ_TRY(fr_check_canonical(ctx, ctx->scalars.as<uint32_t>(), n, reinterpret_cast<int*>(s + kSmallFlag)));
+  }
+  MZ_TRY(fr_range_eval(ctx, ctx->scalars.as<uint32_t>(), n, u_le, reinterpret_cast<uint32_t*>(s + kSmallY),
+                       reinterpret_cast<uint32_t*>(s + kSmallY + 32)));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+int myzkp_fr_quotient(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32],
+                      uint8_t* out_q) {
+  if (!ctx || (!coefs_le && n) || !u_le || !out_y || (n > 1 && !out_q)) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  if (n == 0) {
+    memset(out_y, 0, 32);
+    return MYZKP_OK;
+  }
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+  MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_TRY(fr_check_canonical(ctx, ctx->scalars.as<uint32_t>(), n, reinterpret_cast<int*>(s + kSmallFlag)));
+  MZ_TRY(fr_range_quotient(ctx, ctx->scalars.as<uint32_t>(), n, u_le, nullptr, ctx->scalars2.as<uint32_t>(),
+                           reinterpret_cast<uint32_t*>(s + kSmallY)));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 1) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_q, ctx->scalars2.p, (n - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// Host-side context shared by the translation units of libmyzkp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/myzkp_b200.h"
+#include "g1.cuh"
+
+namespace mz {
+
+// Rows of the resident SRS table: row j holds 2^(8j) * P_i for every SRS point,
+// so that an MSM with window c (a multiple of 8) needs no doublings at all:
+// sum_w 2^(c w) d_w P = sum_w d_w * row[(c/8) w].
+constexpr int kTableStrideBits = 8;
+constexpr int kTableRows = 32;  // 8 * 32 = 256 >= 255 bits (254-bit scalar + sign carry)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    // grow geometrically so repeated slightly-larger calls do not thrash
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace mz
+
+struct myzkp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  // tuning (0 = auto)
+  int window_bits = 0;
+  int segment_len = 0;
+
+  // resident SRS table: kTableRows rows of srs_n affine points (Montgomery)
+  mz::Affine* table = nullptr;
+  size_t srs_n = 0;
+
+  // fixed-base comb table of G for srs_generate: [32][256] affine
+  mz::Affine* gcomb = nullptr;
+
+  // scratch (grow-only)
+  mz::DevBuf scalars;      // staged scalars / coefficients (n * 32 B)
+  mz::DevBuf scalars2;     // quotient / folded coefficients
+  mz::DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
+  mz::DevBuf buckets;      // XYZZ per bucket
+  mz::DevBuf heads, head_keys;
+  mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
+  mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
+  mz::DevBuf small;        // misc small device outputs (flags, y, points)
+  mz::DevBuf xyzz_tmp;     // XYZZ temporaries (SRS generation)
+  void* pinned = nullptr;  // pinned staging for small D2H results
+  size_t pinned_cap = 0;
+};
+
+#define MZ_CUDA_TRY(ctx, expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+      return (_e == cudaErrorMemoryAllocation) ? MYZKP_ERR_OOM : MYZKP_ERR_CUDA;      \
+    }                                                                                 \
+  } while (0)
+
+#define MZ_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != MYZKP_OK) return _r; \
+  } while (0)
+
+#define MZ_LAUNCH_CHECK(ctx)                    \
+  do {                                          \
+    (ctx)->launches++;                          \
+    MZ_CUDA_TRY(ctx, cudaGetLastError());       \
+  } while (0)
+
+namespace mz {
+
+inline int fail(myzkp_ctx* ctx, int code, const char* msg) {
+  ctx->err = msg;
+  return code;
+}
+
+// ---- msm.cu ----
+// MSM of n canonical scalars (device, 32 B LE each) against SRS points
+// [srs_off, srs_off + n); result XYZZ (Montgomery) written to d_out (device).
+int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, XYZZ* d_out);
+// XYZZ (device) -> canonical affine 64 B (device)
+int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
+int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);
+
+// ---- srs.cu ----
+int srs_alloc(myzkp_ctx* ctx, size_t n);
+int srs_build_from_row0(myzkp_ctx* ctx);  // fills rows 1.. from row 0 (Montgomery affine)
+
+// ---- poly.cu ----
+// (h, u^n) of a coefficient range; both canonical 32 B written to device
+int fr_range_eval(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
+                  uint32_t* d_h, uint32_t* d_upow);
+// with c_i = f_{lo+i} + u c_{i+1} and c_n = carry: d_q[i] = c_{i+1} (= q_{lo+i}), *d_c0 = c_0
+// (carry_le == NULL means 0)
+int fr_range_quotient(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
+                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0);
+int fr_fold(myzkp_ctx* ctx, const uint32_t* d_in, size_t n_out, const uint32_t* d_rho, uint32_t* d_out);
+int fr_check_canonical(myzkp_ctx* ctx, const uint32_t* d_in, size_t n, int* d_flag);
+
+}  // namespace mz

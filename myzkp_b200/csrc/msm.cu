@@ -1,0 +1,365 @@
+// Pippenger bucket MSM over the resident SRS table - the GPU form of
+// Polynomial::eval_with_powers_on_curve (polynomial.rs:156-165), which in the
+// reference is N sequential double-and-add scalar multiplications
+// (curve.rs:163-191) of sanitized coefficients (field.rs:260-270).
+//
+// Pipeline (all on the ctx stream, no host round trips):
+//   1. msm_recode      scalar -> W signed c-bit digits; one (bucket key, table
+//                      index | sign) entry per non-zero digit.  Because table
+//                      row j holds 2^(8j) P_i, every window shares ONE set of
+//                      2^(c-1) buckets and no doublings are ever needed.
+//   2. radix sort      entries by bucket key (cub::DeviceRadixSort, c bits).
+//   3. msm_accumulate  fixed-length segments of the sorted entry list, one
+//                      thread each, XYZZ mixed adds; load-balanced for any
+//                      scalar distribution (a heavy bucket just spans segments).
+//   4. msm_merge_heads segments that start inside a bucket hand their first
+//                      partial to the bucket's owner.
+//   5. msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
+//                      running sums, then a tree sum.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ctx.cuh"
+
+namespace mz {
+
+// ---------------------------------------------------------------------------
+// small load/store helpers (16-byte vector accesses)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ Affine load_affine(const Affine* p) {
+  Affine r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
+  r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
+  r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  return r;
+}
+__device__ __forceinline__ void store_xyzz(XYZZ* p, const XYZZ& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) q[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+}
+__device__ __forceinline__ XYZZ load_xyzz(const XYZZ* p) {
+  XYZZ v;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint32_t* s = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint4 a = q[i];
+    s[4 * i] = a.x; s[4 * i + 1] = a.y; s[4 * i + 2] = a.z; s[4 * i + 3] = a.w;
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// 1. signed-digit recode
+// ---------------------------------------------------------------------------
+// digits d_w in (-2^(c-1), 2^(c-1)], sum_w d_w 2^(c w) = scalar.  W*c >= 255
+// guarantees the top window absorbs the last carry for any scalar < 2^254.
+// key = |d| - 1 in [0, 2^(c-1)), or `sentinel` = 2^(c-1) for d == 0 (sorted to
+// the end and ignored).  val = sign << 31 | (row(w) * srs_n + srs_off + i).
+__global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ scalars, size_t n, int c, int W,
+                                                  uint32_t srs_n, uint32_t srs_off, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ vals, int* __restrict__ flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr sc;
+  {
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    sc.v[0] = a.x; sc.v[1] = a.y; sc.v[2] = a.z; sc.v[3] = a.w;
+    sc.v[4] = b.x; sc.v[5] = b.y; sc.v[6] = b.z; sc.v[7] = b.w;
+  }
+  if (!fe_is_canonical(sc)) atomicOr(flag, 1);
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+  const uint32_t rows_per_window = (uint32_t)(c / kTableStrideBits);
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    int bit = w * c;
+    int limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      uint64_t two = sc.v[limb];
+      if (limb + 1 < 8) two |= (uint64_t)sc.v[limb + 1] << 32;
+      raw = (uint32_t)(two >> sh) & mask;
+    }
+    uint32_t d = raw + carry;
+    uint32_t neg = d > half ? 1u : 0u;
+    uint32_t mag = neg ? ((1u << c) - d) : d;
+    carry = neg;
+    uint32_t key = mag ? mag - 1 : half;
+    uint32_t idx = (uint32_t)w * rows_per_window * srs_n + srs_off + (uint32_t)i;
+    keys[(size_t)w * n + i] = key;
+    vals[(size_t)w * n + i] = idx | (neg << 31);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 3. segment accumulate
+// ---------------------------------------------------------------------------
+// Thread t owns sorted entries [t*L, (t+1)*L).  Its first run (bucket of its
+// first entry) may continue a run of the previous segment, so it always goes to
+// heads[t]; every later run starts inside the segment, making this thread the
+// unique first writer of that bucket.  Buckets are pre-zeroed (= infinity).
+constexpr int kAccThreads = 128;
+
+__global__ void __launch_bounds__(kAccThreads, 4)
+    msm_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M, uint32_t L,
+                   uint32_t sentinel, const Affine* __restrict__ tbl, XYZZ* __restrict__ buckets,
+                   XYZZ* __restrict__ heads, uint32_t* __restrict__ head_keys, uint64_t T) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint64_t s = t * L;
+  uint64_t e = s + L < M ? s + L : M;
+  uint32_t cur = keys[s];
+  if (cur >= sentinel) {
+    head_keys[t] = sentinel;
+    return;
+  }
+  head_keys[t] = cur;
+  XYZZ acc = xyzz_inf();
+  bool first_run = true;
+  // software pipeline: the next entry's point is in flight while this one is added
+  uint32_t v = vals[s];
+  Affine pt = load_affine(tbl + (v & 0x7fffffffu));
+  for (uint64_t i = s; i < e; i++) {
+    uint32_t k_next = sentinel, v_next = 0;
+    Affine pt_next;
+    pt_next.x = Fq::zero(); pt_next.y = Fq::zero();
+    if (i + 1 < e) {
+      k_next = keys[i + 1];
+      if (k_next < sentinel) {
+        v_next = vals[i + 1];
+        pt_next = load_affine(tbl + (v_next & 0x7fffffffu));
+      }
+    }
+    if (v >> 31) pt.y = fe_neg(pt.y);
+    xyzz_madd(acc, pt);
+    if (k_next != cur) {
+      if (first_run) store_xyzz(heads + t, acc);
+      else store_xyzz(buckets + cur, acc);
+      first_run = false;
+      acc = xyzz_inf();
+      cur = k_next;
+      if (k_next >= sentinel) break;
+    }
+    v = v_next;
+    pt = pt_next;
+  }
+}
+
+// 4. the first segment whose head belongs to bucket k folds all heads of k in
+__global__ void __launch_bounds__(128) msm_merge_heads(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
+                                                       const uint32_t* __restrict__ head_keys, uint64_t T,
+                                                       uint32_t sentinel) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint32_t k = head_keys[t];
+  if (k >= sentinel) return;
+  if (t > 0 && head_keys[t - 1] == k) return;
+  XYZZ acc = load_xyzz(buckets + k);
+  for (uint64_t j = t; j < T && head_keys[j] == k; j++) {
+    XYZZ h = load_xyzz(heads + j);
+    xyzz_add(acc, h);
+  }
+  store_xyzz(buckets + k, acc);
+}
+
+// ---------------------------------------------------------------------------
+// 5. bucket reduce: sum_{idx} (idx + 1) * B[idx]
+// ---------------------------------------------------------------------------
+// thread j owns buckets [j*Lb, (j+1)*Lb): running sums give A = sum B and
+// S = sum (idx - j*Lb + 1) B; its contribution is S + (j*Lb) * A.
+__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ buckets, uint32_t nb, uint32_t Lb,
+                                                         XYZZ* __restrict__ out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t lo = (uint64_t)j * Lb;
+  if (lo >= nb) return;
+  uint64_t hi = lo + Lb < nb ? lo + Lb : nb;
+  XYZZ run = xyzz_inf(), sum = xyzz_inf();
+  for (uint64_t idx = hi; idx > lo; idx--) {
+    XYZZ b = load_xyzz(buckets + (idx - 1));
+    xyzz_add(run, b);
+    xyzz_add(sum, run);
+  }
+  // sum += lo * run  (MSB-first double-and-add on the small public scalar lo)
+  if (lo != 0 && !xyzz_is_inf(run)) {
+    XYZZ m = xyzz_inf();
+    int top = 63 - __clzll((unsigned long long)lo);
+    for (int bit = top; bit >= 0; bit--) {
+      xyzz_dbl(m);
+      if ((lo >> bit) & 1) xyzz_add(m, run);
+    }
+    xyzz_add(sum, m);
+  }
+  store_xyzz(out + j, sum);
+}
+
+// block-wide tree sum of XYZZ values; out[blockIdx.x] = sum of in[block range]
+constexpr int kTreeThreads = 128;
+__global__ void __launch_bounds__(kTreeThreads) xyzz_tree_reduce(const XYZZ* __restrict__ in, uint64_t n,
+                                                                 XYZZ* __restrict__ out) {
+  __shared__ XYZZ sm[kTreeThreads];
+  uint64_t i = (uint64_t)blockIdx.x * (2 * kTreeThreads) + threadIdx.x;
+  XYZZ acc = xyzz_inf();
+  if (i < n) acc = load_xyzz(in + i);
+  if (i + kTreeThreads < n) {
+    XYZZ b = load_xyzz(in + i + kTreeThreads);
+    xyzz_add(acc, b);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+#pragma unroll 1
+  for (int d = kTreeThreads / 2; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      XYZZ b = sm[threadIdx.x + d];
+      xyzz_add(acc, b);
+      sm[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, acc);
+}
+
+// one thread per point (each does its own Fermat inversion)
+__global__ void xyzz_to_affine_bytes(const XYZZ* in, size_t count, uint32_t* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  XYZZ p = load_xyzz(in + t);
+  Affine a = xyzz_to_affine(p);
+  Fq x = fe_from_mont(a.x), y = fe_from_mont(a.y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    out[t * 16 + i] = x.v[i];
+    out[t * 16 + 8 + i] = y.v[i];
+  }
+}
+
+__global__ void xyzz_set_inf(XYZZ* out) { store_xyzz(out, xyzz_inf()); }
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static int pick_window(const myzkp_ctx* ctx, size_t n) {
+  if (ctx->window_bits == 8 || ctx->window_bits == 16 || ctx->window_bits == 24) return ctx->window_bits;
+  if (n < ((size_t)1 << 11)) return 8;
+  if (n >= ((size_t)1 << 23)) return 24;
+  return 16;
+}
+
+// tree-sum `count` XYZZ values living in buffer `a` (ping-pong with `b`); the
+// single result ends in *d_out
+static int tree_sum(myzkp_ctx* ctx, XYZZ* a, XYZZ* b, uint64_t count, XYZZ* d_out) {
+  while (true) {
+    uint64_t blocks = (count + 2 * kTreeThreads - 1) / (2 * kTreeThreads);
+    XYZZ* dst = (blocks == 1) ? d_out : b;
+    xyzz_tree_reduce<<<(unsigned)blocks, kTreeThreads, 0, ctx->stream>>>(a, count, dst);
+    MZ_LAUNCH_CHECK(ctx);
+    if (blocks == 1) return MYZKP_OK;
+    count = blocks;
+    XYZZ* tmp = a; a = b; b = tmp;
+  }
+}
+
+int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, XYZZ* d_out) {
+  if (n == 0) {
+    xyzz_set_inf<<<1, 1, 0, ctx->stream>>>(d_out);
+    MZ_LAUNCH_CHECK(ctx);
+    return MYZKP_OK;
+  }
+  if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
+  if (srs_off + n > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+
+  const int c = pick_window(ctx, n);
+  const int W = (255 + c - 1) / c;
+  const uint32_t nb = 1u << (c - 1);
+  const uint64_t M = (uint64_t)W * n;
+  if (M >= (1ull << 32)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "MSM too large for 32-bit entry indices");
+
+  MZ_CUDA_TRY(ctx, ctx->keys_a.ensure(M * 4));
+  MZ_CUDA_TRY(ctx, ctx->keys_b.ensure(M * 4));
+  MZ_CUDA_TRY(ctx, ctx->vals_a.ensure(M * 4));
+  MZ_CUDA_TRY(ctx, ctx->vals_b.ensure(M * 4));
+  MZ_CUDA_TRY(ctx, ctx->buckets.ensure((size_t)nb * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 512);
+
+  uint32_t* keys_a = ctx->keys_a.as<uint32_t>();
+  uint32_t* keys_b = ctx->keys_b.as<uint32_t>();
+  uint32_t* vals_a = ctx->vals_a.as<uint32_t>();
+  uint32_t* vals_b = ctx->vals_b.as<uint32_t>();
+
+  // 1. recode
+  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, (uint32_t)ctx->srs_n,
+                                                                   (uint32_t)srs_off, keys_a, vals_a, flag);
+  MZ_LAUNCH_CHECK(ctx);
+
+  // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit)
+  size_t tmp_bytes = 0;
+  MZ_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, M, 0, c,
+                                                   ctx->stream));
+  MZ_CUDA_TRY(ctx, ctx->sort_tmp.ensure(tmp_bytes));
+  MZ_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, keys_a, keys_b, vals_a, vals_b, M, 0,
+                                                   c, ctx->stream));
+  ctx->launches += (c + 7) / 8 + 2;  // onesweep: histogram + scan + one kernel per 8-bit pass
+
+  // 3. accumulate
+  uint32_t L = (uint32_t)ctx->segment_len;
+  if (L == 0) {
+    uint64_t target_threads = (uint64_t)ctx->sm_count * 512 * 8;
+    uint64_t l = (M + target_threads - 1) / target_threads;
+    L = (uint32_t)(l < 8 ? 8 : (l > 256 ? 256 : l));
+  }
+  const uint64_t T = (M + L - 1) / L;
+  MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
+  MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+  msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+      keys_b, vals_b, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+      ctx->head_keys.as<uint32_t>(), T);
+  MZ_LAUNCH_CHECK(ctx);
+
+  // 4. merge segment heads
+  msm_merge_heads<<<(unsigned)((T + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+                                                                        ctx->head_keys.as<uint32_t>(), T, nb);
+  MZ_LAUNCH_CHECK(ctx);
+
+  // 5. bucket reduce + tree sum
+  uint32_t Lb = nb >= (1u << 20) ? 64 : 8;
+  uint32_t nchunks = (nb + Lb - 1) / Lb;
+  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
+  msm_bucket_reduce<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), nb, Lb,
+                                                                    ctx->red_a.as<XYZZ>());
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out));
+  return MYZKP_OK;
+}
+
+int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64) {
+  if (count == 0) return MYZKP_OK;
+  xyzz_to_affine_bytes<<<(unsigned)((count + 31) / 32), 32, 0, ctx->stream>>>(d_in, count,
+                                                                              reinterpret_cast<uint32_t*>(d_out64));
+  MZ_LAUNCH_CHECK(ctx);
+  return MYZKP_OK;
+}
+
+int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64) {
+  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((k + 2) * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->red_b.ensure((k / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+  XYZZ* res = reinterpret_cast<XYZZ*>(ctx->small.as<uint8_t>() + 1024);
+  if (k == 0) {
+    xyzz_set_inf<<<1, 1, 0, ctx->stream>>>(res);
+    MZ_LAUNCH_CHECK(ctx);
+  } else {
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->red_a.p, d_partials, k * sizeof(XYZZ), cudaMemcpyDeviceToDevice, ctx->stream));
+    MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), k, res));
+  }
+  return xyzz_to_bytes(ctx, res, 1, d_out64);
+}
+
+}  // namespace mz

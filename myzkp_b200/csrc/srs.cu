@@ -1,0 +1,280 @@
+// Resident SRS table (PublicKeyKZG.powers_1, kzg.rs:8-11) and its generation.
+//
+// setup_kzg (kzg.rs:27-40) computes powers_1[i] = [alpha^i]G with one
+// double-and-add scalar multiplication per point.  Here: alpha^i on the device
+// (Fr), a fixed-base comb of G (32 x 255 precomputed multiples, 8-bit digits,
+// <= 32 mixed adds per point), batched to-affine, and then the table rows
+// row[j][i] = 2^(8j) * P_i that let every MSM window reuse one bucket set.
+#include "ctx.cuh"
+
+namespace mz {
+
+__device__ __forceinline__ Fq load_fq(const uint32_t* p) {
+  Fq r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void store_fq(uint32_t* p, const Fq& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// canonical LE bytes -> Montgomery affine (row 0); flags non-canonical input
+__global__ void srs_import(const uint32_t* in, size_t n, Affine* row0, int* flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq x = load_fq(in + i * 16), y = load_fq(in + i * 16 + 8);
+  if (!fe_is_canonical(x) || !fe_is_canonical(y)) atomicOr(flag, 1);
+  Affine a;
+  a.x = fe_to_mont(x);
+  a.y = fe_to_mont(y);
+  row0[i] = a;
+}
+
+// Montgomery affine -> canonical LE bytes
+__global__ void srs_export(const Affine* row0, size_t n, uint32_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine a = row0[i];
+  store_fq(out + i * 16, fe_from_mont(a.x));
+  store_fq(out + i * 16 + 8, fe_from_mont(a.y));
+}
+
+// rows 1..rows-1 from row 0: Jacobian doubling chain, one batched inversion per point
+__global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int rows) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine p = tbl[i];
+  if (affine_is_inf(p)) {
+    for (int j = 1; j < rows; j++) tbl[(size_t)j * n + i] = p;
+    return;
+  }
+  Jac cur;
+  cur.x = p.x; cur.y = p.y; cur.z = Fq::one();
+  Fq zs[kTableRows - 1];
+  Fq pref[kTableRows - 1];
+  for (int j = 1; j < rows; j++) {
+#pragma unroll 1
+    for (int d = 0; d < kTableStrideBits; d++) jac_dbl(cur);
+    Affine un;  // unnormalised X, Y parked in the table slot
+    un.x = cur.x; un.y = cur.y;
+    tbl[(size_t)j * n + i] = un;
+    zs[j - 1] = cur.z;
+    pref[j - 1] = (j == 1) ? cur.z : fe_mul(pref[j - 2], cur.z);
+  }
+  Fq inv = fe_inv(pref[rows - 2]);
+  for (int k = rows - 2; k >= 0; k--) {
+    Fq zinv = (k > 0) ? fe_mul(inv, pref[k - 1]) : inv;
+    inv = fe_mul(inv, zs[k]);
+    Fq z2 = fe_sqr(zinv);
+    Affine un = tbl[(size_t)(k + 1) * n + i];
+    Affine o;
+    o.x = fe_mul(un.x, z2);
+    o.y = fe_mul(un.y, fe_mul(z2, zinv));
+    tbl[(size_t)(k + 1) * n + i] = o;
+  }
+}
+
+// XYZZ -> Montgomery affine, 8 points per thread share one inversion
+constexpr int kBatchAffine = 8;
+__global__ void __launch_bounds__(128) batch_to_affine(const XYZZ* in, size_t n, Affine* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * kBatchAffine;
+  if (lo >= n) return;
+  int cnt = (n - lo) < (size_t)kBatchAffine ? (int)(n - lo) : kBatchAffine;
+  Fq pref[kBatchAffine];
+  Fq acc = Fq::one();
+  for (int k = 0; k < cnt; k++) {
+    Fq z = in[lo + k].zzz;
+    if (z.is_zero()) z = Fq::one();  // infinity: keep the product invertible
+    acc = fe_mul(acc, z);
+    pref[k] = acc;
+  }
+  Fq inv = fe_inv(acc);
+  for (int k = cnt - 1; k >= 0; k--) {
+    XYZZ p = in[lo + k];
+    Affine o;
+    if (xyzz_is_inf(p)) {
+      o.x = Fq::zero(); o.y = Fq::zero();
+    } else {
+      Fq zi = (k > 0) ? fe_mul(inv, pref[k - 1]) : inv;
+      inv = fe_mul(inv, p.zzz);
+      o = xyzz_to_affine_with_inv(p, zi);
+    }
+    out[lo + k] = o;
+  }
+}
+
+// comb[j*256 + d] = d * base2[j]  (base2[j] = 2^(8j) G, affine), d = 0..255 as XYZZ
+__global__ void srs_comb_multiples(const Affine* base2, XYZZ* out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kTableRows * 256) return;
+  int j = idx >> 8, d = idx & 255;
+  Affine b = base2[j];
+  XYZZ acc = xyzz_inf();
+  for (int bit = 7; bit >= 0; bit--) {
+    xyzz_dbl(acc);
+    if ((d >> bit) & 1) xyzz_madd(acc, b);
+  }
+  out[idx] = acc;
+}
+
+// scalars[i] = alpha^(first+i) canonical
+__global__ void srs_alpha_powers(const uint32_t* alpha_canon, size_t first, size_t n, uint32_t* scalars) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr a;
+#pragma unroll
+  for (int k = 0; k < 8; k++) a.v[k] = alpha_canon[k];
+  a = fe_to_mont(a);
+  Fr r = fe_from_mont(fe_pow_u64(a, (uint64_t)(first + i)));
+  uint4* q = reinterpret_cast<uint4*>(scalars + i * 8);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// out[i] = [scalars[i]] G via the comb (unsigned 8-bit digits)
+__global__ void __launch_bounds__(128) srs_fixed_base(const uint32_t* scalars, size_t n, const Affine* comb,
+                                                      XYZZ* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) s[k] = scalars[i * 8 + k];
+  XYZZ acc = xyzz_inf();
+#pragma unroll 1
+  for (int j = 0; j < kTableRows; j++) {
+    uint32_t d = (s[j >> 2] >> ((j & 3) * 8)) & 255u;
+    if (d) xyzz_madd(acc, comb[j * 256 + d]);
+  }
+  out[i] = acc;
+}
+
+__global__ void srs_set_generator(Affine* out) {
+  Affine g;
+  Fq one = Fq::one();
+  g.x = one;                // G = (1, 2)  (bn128.rs:185-188)
+  g.y = fe_dbl(one);
+  out[0] = g;
+}
+
+// ---------------------------------------------------------------------------
+int srs_alloc(myzkp_ctx* ctx, size_t n) {
+  if (ctx->table) {
+    cudaFree(ctx->table);
+    ctx->table = nullptr;
+    ctx->srs_n = 0;
+  }
+  if (n == 0) return MYZKP_OK;
+  if ((uint64_t)n * kTableRows >= (1ull << 31)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "SRS too large (n * 32 must be < 2^31)");
+  MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->table, n * kTableRows * sizeof(Affine)));
+  ctx->srs_n = n;
+  return MYZKP_OK;
+}
+
+int srs_build_from_row0(myzkp_ctx* ctx) {
+  size_t n = ctx->srs_n;
+  if (n == 0) return MYZKP_OK;
+  srs_build_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->table, n, kTableRows);
+  MZ_LAUNCH_CHECK(ctx);
+  return MYZKP_OK;
+}
+
+static int ensure_gcomb(myzkp_ctx* ctx) {
+  if (ctx->gcomb) return MYZKP_OK;
+  // base2[j] = 2^(8j) G through the same row builder (n = 1)
+  Affine* base2 = nullptr;
+  MZ_CUDA_TRY(ctx, cudaMalloc(&base2, kTableRows * sizeof(Affine)));
+  srs_set_generator<<<1, 1, 0, ctx->stream>>>(base2);
+  MZ_LAUNCH_CHECK(ctx);
+  srs_build_rows<<<1, 128, 0, ctx->stream>>>(base2, 1, kTableRows);
+  MZ_LAUNCH_CHECK(ctx);
+  const int total = kTableRows * 256;
+  MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((size_t)total * sizeof(XYZZ)));
+  srs_comb_multiples<<<(total + 127) / 128, 128, 0, ctx->stream>>>(base2, ctx->xyzz_tmp.as<XYZZ>());
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->gcomb, (size_t)total * sizeof(Affine)));
+  unsigned blocks = (unsigned)((total + kBatchAffine * 128 - 1) / (kBatchAffine * 128));
+  batch_to_affine<<<blocks, 128, 0, ctx->stream>>>(ctx->xyzz_tmp.as<XYZZ>(), total, ctx->gcomb);
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(base2);
+  return MYZKP_OK;
+}
+
+}  // namespace mz
+
+using namespace mz;
+
+extern "C" int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le, size_t n) {
+  if (!ctx || (!affine_xy_le && n)) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_TRY(srs_alloc(ctx, n));
+  if (n == 0) return MYZKP_OK;
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 64));
+  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 512);
+  MZ_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, affine_xy_le, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  srs_import<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->table, flag);
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_TRY(srs_build_from_row0(ctx));
+  int h_flag = 0;
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_flag) {
+    srs_alloc(ctx, 0);
+    return fail(ctx, MYZKP_ERR_NONCANONICAL, "SRS coordinate >= p");
+  }
+  return MYZKP_OK;
+}
+
+extern "C" int myzkp_srs_generate_g1(myzkp_ctx* ctx, const uint8_t alpha_le[32], size_t first, size_t n) {
+  if (!ctx || !alpha_le) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_TRY(ensure_gcomb(ctx));
+  MZ_TRY(srs_alloc(ctx, n));
+  if (n == 0) return MYZKP_OK;
+  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(s, alpha_le, 32, cudaMemcpyHostToDevice, ctx->stream));
+  // chunked so the XYZZ temporaries stay bounded
+  const size_t chunk = (size_t)1 << 22;
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure((n < chunk ? n : chunk) * 32));
+  MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((n < chunk ? n : chunk) * sizeof(XYZZ)));
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t m = n - off < chunk ? n - off : chunk;
+    unsigned blocks = (unsigned)((m + 127) / 128);
+    srs_alpha_powers<<<blocks, 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(s), first + off, m,
+                                                      ctx->scalars.as<uint32_t>());
+    MZ_LAUNCH_CHECK(ctx);
+    srs_fixed_base<<<blocks, 128, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), m, ctx->gcomb,
+                                                    ctx->xyzz_tmp.as<XYZZ>());
+    MZ_LAUNCH_CHECK(ctx);
+    unsigned bblocks = (unsigned)((m + kBatchAffine * 128 - 1) / (kBatchAffine * 128));
+    batch_to_affine<<<bblocks, 128, 0, ctx->stream>>>(ctx->xyzz_tmp.as<XYZZ>(), m, ctx->table + off);
+    MZ_LAUNCH_CHECK(ctx);
+  }
+  MZ_TRY(srs_build_from_row0(ctx));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MYZKP_OK;
+}
+
+extern "C" int myzkp_srs_read_g1(myzkp_ctx* ctx, size_t off, size_t n, uint8_t* out) {
+  if (!ctx || (!out && n)) return MYZKP_ERR_INVALID_ARG;
+  if (off + n > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "srs_read out of range");
+  if (n == 0) return MYZKP_OK;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 64));
+  srs_export<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->table + off, n, ctx->scalars.as<uint32_t>());
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->scalars.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MYZKP_OK;
+}
+
+extern "C" size_t myzkp_srs_len(const myzkp_ctx* ctx) { return ctx ? ctx->srs_n : 0; }

@@ -1,0 +1,44 @@
+"""Host-side mirror of gemini.rs:51-114 (split_and_fold + commit_gemini)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from .context import R_MOD, bytes_to_int
+from .kzg import G1Point, Polynomial, PublicKeyKZG
+
+
+class SplitFoldError(ValueError):
+    """gemini.rs:15-32."""
+
+
+def _check(n: int, n_rhos: int):
+    if n == 0 or (n & (n - 1)):
+        raise SplitFoldError(f"coefs.len() must be a power of two, but got {n}")
+    log2_n = n.bit_length() - 1
+    if n_rhos != log2_n:
+        raise SplitFoldError(f"points.len() must be {log2_n}, but got {n_rhos}")
+
+
+def split_and_fold_commit(coef, rhos: Sequence[int], pk: PublicKeyKZG, want_folds: bool = False):
+    """split_and_fold (gemini.rs:51-103) fused with commit_gemini (gemini.rs:112-114):
+    the folds stay in HBM and each level is committed where it lies."""
+    n = len(coef)
+    _check(n, len(rhos))
+    wire = coef if isinstance(coef, np.ndarray) else [int(c) % R_MOD for c in coef]
+    res = pk.ctx.gemini_fold_commit(wire, [int(r) % R_MOD for r in rhos], want_folds=want_folds)
+    if want_folds:
+        pts, folds = res
+        polys, off, ln = [], 0, n // 2
+        while ln >= 1:
+            polys.append(Polynomial([bytes_to_int(folds[off + i]) for i in range(ln)]))
+            off += ln
+            ln //= 2
+        return [G1Point._from_tuple(p) for p in pts], polys
+    return [G1Point._from_tuple(p) for p in res]
+
+
+def commit_gemini(polys: Sequence[Polynomial], pk: PublicKeyKZG) -> List[G1Point]:
+    """gemini.rs:112-114: one commit_kzg per polynomial."""
+    return [G1Point._from_tuple(pk.ctx.commit(p._wire())) for p in polys]

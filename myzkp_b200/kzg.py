@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference's KZG surface for the hot path.
+
+Same names, argument meaning and error behaviour as
+myzkp/src/modules/algebra/kzg.rs (setup_kzg :27-40, commit_kzg :57-59,
+open_kzg :61-72) and polynomial.rs (Polynomial{coef} low->high, :69-74), with
+the work done by libmyzkp_b200.so on the GPU.  Scalars are Python ints (the
+reference's FqOrder values); they are sanitized to [0, r) before they cross
+the ABI, exactly where the reference sanitizes (polynomial.rs:162).
+"""
+from __future__ import annotations
+
+import secrets
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .context import Context, R_MOD, P_MOD
+
+
+class G1Point:
+    """EllipticCurvePoint<Fq, BN128Curve> (curve/curve.rs:17-46): affine; infinity = (None, None)."""
+
+    __slots__ = ("x", "y")
+
+    def __init__(self, x: Optional[int] = None, y: Optional[int] = None):
+        self.x = None if x is None else int(x) % P_MOD
+        self.y = None if y is None else int(y) % P_MOD
+
+    @staticmethod
+    def point_at_infinity() -> "G1Point":
+        return G1Point(None, None)
+
+    def is_point_at_infinity(self) -> bool:
+        return self.x is None or self.y is None
+
+    @staticmethod
+    def _from_tuple(t) -> "G1Point":
+        return G1Point(None, None) if t is None else G1Point(t[0], t[1])
+
+    def as_tuple(self):
+        return None if self.is_point_at_infinity() else (self.x, self.y)
+
+    def __eq__(self, o):
+        return isinstance(o, G1Point) and self.as_tuple() == o.as_tuple()
+
+    def __repr__(self):
+        return f"G1Point({self.as_tuple()})"
+
+
+class BN128:
+    """curve/bn128.rs:183-212 (G1 side only)."""
+
+    @staticmethod
+    def generator_g1() -> G1Point:
+        return G1Point(1, 2)
+
+    @staticmethod
+    def order() -> int:
+        return R_MOD
+
+
+class Polynomial:
+    """Polynomial<FqOrder> (polynomial.rs:69-74): `coef` in increasing degree.
+
+    `coef` may be a list of ints (any sign; sanitized like field.rs:260-270) or
+    an (n,32) uint8 / (n,4) uint64 array of canonical little-endian scalars.
+    """
+
+    def __init__(self, coef):
+        self.coef = coef
+
+    def _wire(self):
+        if isinstance(self.coef, np.ndarray):
+            return self.coef
+        return [int(c) % R_MOD for c in self.coef]  # sanitize (polynomial.rs:162)
+
+    def __len__(self):
+        return len(self.coef)
+
+
+class PublicKeyKZG:
+    """kzg.rs:8-11.  powers_1 lives on the GPU as the resident SRS table;
+    powers_2 (G2) is verifier-side and out of scope."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    @property
+    def powers_1(self) -> List[G1Point]:
+        return [G1Point._from_tuple(t) for t in self.ctx.srs_read(0, self.ctx.srs_len)]
+
+    def __len__(self):
+        return self.ctx.srs_len
+
+
+class ProofKZG:
+    """kzg.rs:15-18."""
+
+    def __init__(self, y: int, w: G1Point):
+        self.y = y
+        self.w = w
+
+
+CommitmentKZG = G1Point
+
+
+def setup_kzg(g1: G1Point, g2=None, max_d: int = 0, *, alpha: Optional[int] = None, ctx: Optional[Context] = None,
+              device: int = 0) -> PublicKeyKZG:
+    """kzg.rs:27-40: max_d + 1 powers [alpha^i]g1.  The reference draws alpha from
+    an unseeded thread_rng (field.rs:198-206); pass `alpha` for reproducibility.
+    Only the standard generator is supported on the device path; any other base
+    point is handled by loading explicit powers with PublicKeyKZG/ctx.srs_load."""
+    if g1 != BN128.generator_g1():
+        raise ValueError("setup_kzg on the GPU path generates powers of BN128::generator_g1(); load other SRS with Context.srs_load")
+    if alpha is None:
+        alpha = secrets.randbelow(R_MOD)
+    ctx = ctx or Context(device)
+    ctx.srs_generate(alpha, max_d + 1)
+    return PublicKeyKZG(ctx)
+
+
+def commit_kzg(f: Polynomial, pk: PublicKeyKZG) -> CommitmentKZG:
+    """kzg.rs:57-59.  Raises (reference: index panic, polynomial.rs:162) if f is longer than the SRS."""
+    return G1Point._from_tuple(pk.ctx.commit(f._wire()))
+
+
+def open_kzg(f: Polynomial, u: int, pk: PublicKeyKZG) -> ProofKZG:
+    """kzg.rs:61-72."""
+    y, w = pk.ctx.open(f._wire(), int(u) % R_MOD)
+    return ProofKZG(y, G1Point._from_tuple(w))

@@ -1,0 +1,66 @@
+"""Generates tests/golden/kzg_golden.json with the FAITHFUL oracle path
+(oracle/myzkp_oracle.py: affine double-and-add with ext-Euclid inversions, naive
+MSM, schoolbook division - the restatement of kzg.rs / polynomial.rs / curve.rs).
+Run from the repo root:  python tests/golden/gen_golden.py
+"""
+import json
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import myzkp_oracle as o  # noqa: E402
+from myzkp_oracle import Fr, Polynomial  # noqa: E402
+
+
+def pt(p):
+    t = p.affine_ints()
+    return None if t is None else [str(t[0]), str(t[1])]
+
+
+def main():
+    rnd = random.Random(0xB200)
+    cases = []
+    g = o.generator_g1()
+    specs = [
+        ("test_kzg_poly", 123456789, [6, 11, 6, 1], 5),
+        ("n1", 987654321, [rnd.randrange(o.R_MOD)], rnd.randrange(o.R_MOD)),
+        ("n2", 55555, [rnd.randrange(o.R_MOD) for _ in range(2)], rnd.randrange(o.R_MOD)),
+        ("n16", rnd.randrange(o.R_MOD), [rnd.randrange(o.R_MOD) for _ in range(16)], rnd.randrange(o.R_MOD)),
+        ("n33_bytes", rnd.randrange(o.R_MOD), [rnd.randrange(256) for _ in range(33)], rnd.randrange(o.R_MOD)),
+        ("n48_zeros_and_edges", rnd.randrange(o.R_MOD),
+         [0, 1, o.R_MOD - 1, 0, 2, o.R_MOD - 2] + [rnd.choice([0, rnd.randrange(o.R_MOD)]) for _ in range(42)], 0),
+        ("n64", rnd.randrange(o.R_MOD), [rnd.randrange(o.R_MOD) for _ in range(64)], rnd.randrange(o.R_MOD)),
+    ]
+    for name, alpha, coefs, u in specs:
+        pk = o.setup_kzg(g, len(coefs) - 1, alpha)
+        f = Polynomial([Fr(c) for c in coefs])
+        c = o.commit_kzg(f, pk)
+        pr = o.open_kzg(f, Fr(u), pk)
+        cases.append({
+            "name": name, "alpha": str(alpha), "coefs": [str(x) for x in coefs], "u": str(u),
+            "srs": [pt(p) for p in pk.powers_1],
+            "commit": pt(c), "y": str(pr.y.sanitize().value), "w": pt(pr.w),
+        })
+        print(name, "done", file=sys.stderr)
+    # Gemini: test_gemini coefficients (gemini.rs:294-297) and a random 16
+    gem = []
+    for name, alpha, coefs, rhos in [
+        ("test_gemini", 424242, list(range(1, 9)), [2, 3, 4]),
+        ("book_example", 424242, list(range(1, 9)), [1, 2, 3]),
+        ("n16", rnd.randrange(o.R_MOD), [rnd.randrange(o.R_MOD) for _ in range(16)], [rnd.randrange(o.R_MOD) for _ in range(4)]),
+    ]:
+        pk = o.setup_kzg(g, len(coefs) - 1, alpha)
+        fs = o.split_and_fold([Fr(c) for c in coefs], [Fr(r) for r in rhos])
+        cm = o.commit_gemini(fs, pk)
+        gem.append({"name": name, "alpha": str(alpha), "coefs": [str(x) for x in coefs], "rhos": [str(x) for x in rhos],
+                    "folds": [[str(v) for v in p.canonical()] for p in fs], "commitments": [pt(p) for p in cm]})
+        print(name, "done", file=sys.stderr)
+    out = {"generator": "tests/golden/gen_golden.py (faithful oracle path)", "kzg": cases, "gemini": gem}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_golden.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,46 @@
+"""CPU: libmyzkp_b200.so loads and exports every symbol include/myzkp_b200.h declares
+(no compute calls - there is no GPU here), and the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "myzkp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(myzkp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from myzkp_b200 import _lib
+
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/myzkp_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import myzkp_b200
+
+    with pytest.raises(RuntimeError):
+        myzkp_b200.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "myzkp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "myzkp_oracle" not in text and "oracle/" not in text.replace("the oracle", ""), f

@@ -1,0 +1,31 @@
+"""CPU: the committed golden vectors agree with the oracle's O(N) expected-value
+path (the path used for sizes the faithful oracle cannot reach)."""
+import json
+import os
+
+import myzkp_oracle as o
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kzg_golden.json")))
+
+
+def _pt(p):
+    return None if p is None else (int(p[0]), int(p[1]))
+
+
+def test_golden_kzg_matches_expected_value_path():
+    for case in G["kzg"]:
+        alpha, coefs, u = int(case["alpha"]), [int(c) for c in case["coefs"]], int(case["u"])
+        assert o.expected_commit(coefs, alpha) == _pt(case["commit"]), case["name"]
+        y, w = o.expected_open(coefs, u, alpha)
+        assert y == int(case["y"]) and w == _pt(case["w"]), case["name"]
+        for i, p in enumerate(case["srs"]):
+            assert o.fast_mul(pow(alpha, i, o.R_MOD)) == _pt(p)
+
+
+def test_golden_gemini_matches_fold_ints():
+    for case in G["gemini"]:
+        coefs, rhos, alpha = [int(c) for c in case["coefs"]], [int(r) for r in case["rhos"]], int(case["alpha"])
+        folds = o.fold_ints(coefs, rhos)
+        assert [[int(v) for v in f] for f in case["folds"]] == folds
+        for f, c in zip(folds, case["commitments"]):
+            assert o.expected_commit(f, alpha) == _pt(c)

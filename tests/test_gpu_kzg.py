@@ -1,0 +1,187 @@
+"""GPU parity: setup / commit / open / Gemini through the C ABI vs the oracle and the golden vectors."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import myzkp_oracle as o
+from myzkp_oracle import Fr
+
+import myzkp_b200 as mz
+from myzkp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+R = o.R_MOD
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kzg_golden.json")))
+
+
+def _pt(p):
+    return None if p is None else (int(p[0]), int(p[1]))
+
+
+def test_golden_kzg_vectors(ctx):
+    """setup -> commit -> open against vectors produced by the faithful oracle."""
+    for case in G["kzg"]:
+        alpha, coefs, u = int(case["alpha"]), [int(c) for c in case["coefs"]], int(case["u"])
+        pk = mz.setup_kzg(mz.BN128.generator_g1(), None, len(coefs) - 1, alpha=alpha, ctx=ctx)
+        assert [p.as_tuple() for p in pk.powers_1] == [_pt(p) for p in case["srs"]], case["name"]
+        c = mz.commit_kzg(mz.Polynomial(coefs), pk)
+        assert c.as_tuple() == _pt(case["commit"]), case["name"]
+        pr = mz.open_kzg(mz.Polynomial(coefs), u, pk)
+        assert pr.y == int(case["y"]) and pr.w.as_tuple() == _pt(case["w"]), case["name"]
+
+
+def test_golden_gemini_vectors(ctx):
+    for case in G["gemini"]:
+        coefs, rhos, alpha = [int(c) for c in case["coefs"]], [int(r) for r in case["rhos"]], int(case["alpha"])
+        pk = mz.setup_kzg(mz.BN128.generator_g1(), None, len(coefs) - 1, alpha=alpha, ctx=ctx)
+        cms, polys = mz.split_and_fold_commit(coefs, rhos, pk, want_folds=True)
+        assert [c.as_tuple() for c in cms] == [_pt(p) for p in case["commitments"]], case["name"]
+        assert [list(p.coef) for p in polys] == [[int(v) for v in f] for f in case["folds"][1:]]
+        # commit_gemini on explicit polynomials (gemini.rs:112-114)
+        all_polys = [mz.Polynomial(coefs)] + polys
+        assert [c.as_tuple() for c in mz.commit_gemini(all_polys, pk)] == [_pt(p) for p in case["commitments"]]
+    with pytest.raises(mz.SplitFoldError):
+        mz.split_and_fold_commit([1, 2, 3], [1], pk)
+    with pytest.raises(mz.SplitFoldError):
+        mz.split_and_fold_commit([1, 2, 3, 4], [1], pk)
+
+
+def test_config1_2pow10_vs_faithful_oracle_sample(ctx):
+    """BASELINE config 1 (degree 2^10): SRS spot-checked against the faithful scalar-mul,
+    commit/open against the algebraic expected value (validated vs the faithful path in the CPU suite)."""
+    n = 1 << 10
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    u = synth.random_scalar(synth.SEED_OPEN)
+    coefs = synth.random_scalars(n, synth.SEED_SCALARS + 10)
+    ints = synth.limbs_to_ints(coefs)
+    pk = mz.setup_kzg(mz.BN128.generator_g1(), None, n - 1, alpha=alpha, ctx=ctx)
+    assert len(pk) == n
+    g = o.generator_g1()
+    for i in (0, 1, 2, 513, n - 1):
+        assert ctx.srs_read(i, 1)[0] == (g * pow(alpha, i, R)).affine_ints()
+    srs = ctx.srs_read(0, n)
+    assert srs[:64] == [o.fast_mul(pow(alpha, i, R)) for i in range(64)]
+    assert mz.commit_kzg(mz.Polynomial(coefs), pk).as_tuple() == o.expected_commit(ints, alpha)
+    pr = mz.open_kzg(mz.Polynomial(coefs), u, pk)
+    assert (pr.y, pr.w.as_tuple()) == o.expected_open(ints, u, alpha)
+    # faithful naive MSM on a 48-coefficient prefix (seconds on the CPU)
+    pk_small = o.PublicKeyKZG([o.G1Point.new(o.Fq(x), o.Fq(y)) for x, y in srs[:48]])
+    f_small = o.Polynomial([Fr(c) for c in ints[:48]])
+    assert mz.commit_kzg(mz.Polynomial(ints[:48]), pk).as_tuple() == o.commit_kzg(f_small, pk_small).affine_ints()
+
+
+@pytest.mark.parametrize("logn", [16, 20])
+def test_commit_open_large_vs_expected_value(ctx, logn):
+    """BASELINE configs 2 and 3 on one GPU."""
+    n = 1 << logn
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    u = synth.random_scalar(synth.SEED_OPEN)
+    coefs = synth.random_scalars(n, synth.SEED_SCALARS + logn)
+    ints = synth.limbs_to_ints(coefs)
+    ctx.srs_generate(alpha, n)
+    for i in (0, 1, n // 3, n - 1):
+        assert ctx.srs_read(i, 1)[0] == o.fast_mul(pow(alpha, i, R))
+    assert ctx.commit(coefs) == o.expected_commit(ints, alpha)
+    y, w = ctx.open(coefs, u)
+    assert (y, w) == o.expected_open(ints, u, alpha)
+    # quotient coefficients themselves
+    yq, q = ctx.fr_quotient(coefs, u)
+    ey, eq = o.synthetic_division(ints, u)
+    assert yq == ey
+    assert synth.limbs_to_ints(q.view(np.uint64).reshape(-1, 4)) == eq
+    assert ctx.fr_eval(coefs, u) == ey
+
+
+def test_window_sizes_and_segments_agree(ctx):
+    n = 5000  # not a power of two
+    alpha = 0xABCDEF123456789
+    coefs = synth.random_scalars(n, 99)
+    ints = synth.limbs_to_ints(coefs)
+    ctx.srs_generate(alpha, n)
+    exp = o.expected_commit(ints, alpha)
+    try:
+        for c in (8, 16, 24):
+            for seg in (0, 1, 7, 1000):
+                ctx.set_msm_params(c, seg)
+                assert ctx.commit(coefs) == exp, (c, seg)
+    finally:
+        ctx.set_msm_params(0, 0)
+
+
+def test_scalar_distributions(ctx):
+    """byte-valued scalars (das/avail.rs:93, das/eigenda.rs:96), zeros, all-equal, r-1, P/-P cancellation."""
+    n = 1 << 12
+    alpha = 31337
+    ctx.srs_generate(alpha, n)
+    rnd = random.Random(5)
+    dists = {
+        "bytes": [rnd.randrange(256) for _ in range(n)],
+        "zeros10": [0 if rnd.random() < 0.1 else rnd.randrange(R) for _ in range(n)],
+        "all_zero": [0] * n,
+        "all_one": [1] * n,
+        "all_rm1": [R - 1] * n,
+        "single": [0] * (n - 1) + [5],
+        "two_pow": [1 << rnd.randrange(254) for _ in range(n)],
+        "half_windows": [sum((1 << 15) << (16 * w) for w in range(15))] * n,
+    }
+    for name, sc in dists.items():
+        exp = o.expected_commit(sc, alpha)
+        for c in (8, 16, 24):
+            ctx.set_msm_params(c, 0)
+            assert ctx.commit(sc) == exp, (name, c)
+    ctx.set_msm_params(0, 0)
+    # SRS with repeated points, P / -P pairs and infinity: load explicit points
+    base = [o.fast_mul(k) for k in (3, 3, 5, 7)]
+    neg = lambda p: (p[0], o.P_MOD - p[1])
+    pts = [base[0], base[1], neg(base[0]), None, base[2], neg(base[2]), base[3], base[3]]
+    ctx.srs_load(pts)
+    assert ctx.srs_read(0, 8) == pts
+    sc = [2, 2, 4, 99, 6, 6, 1, R - 1]  # 2*3G + 2*3G - 4*3G + 0 + 6*5G - 6*5G + 7G - 7G = inf
+    assert ctx.commit(sc) is None
+    sc = [1, 1, 0, 5, 0, 0, 0, 0]
+    assert ctx.commit(sc) == o.fast_mul(6)  # P + P must double
+
+
+def test_edge_cases_and_errors(ctx):
+    alpha = 4242
+    ctx.srs_generate(alpha, 8)
+    assert ctx.commit([]) is None  # empty polynomial -> infinity
+    assert ctx.commit([0, 0, 0]) is None
+    y, w = ctx.open([9], 5)  # constant: W = infinity, y = f_0 (polynomial.rs:372-374)
+    assert (y, w) == (9, None)
+    assert ctx.open([], 5) == (0, None)
+    y, w = ctx.open([3, 0, 0, 1], 0)  # u = 0
+    assert (y, w) == o.expected_open([3, 0, 0, 1], 0, alpha)
+    coefs = [1, 2, 3, 4, 5, 6, 7, 8]
+    assert ctx.open(coefs, alpha) [0] == o.synthetic_division(coefs, alpha)[0]  # u == alpha still opens
+    with pytest.raises(RuntimeError):  # longer than the SRS: reference panics (polynomial.rs:162)
+        ctx.commit(list(range(9)))
+    with pytest.raises(RuntimeError):  # non-canonical scalar
+        ctx.commit(np.frombuffer(int(R).to_bytes(32, "little"), dtype=np.uint8).reshape(1, 32).copy())
+    with pytest.raises(RuntimeError):
+        ctx.srs_load([(o.P_MOD, 2)])
+    ctx.srs_generate(alpha, 8)
+    assert ctx.commit([R - 1]) == (1, o.P_MOD - 2)
+
+
+def test_linearity_and_shift_properties_full_size(ctx):
+    """Size-independent properties at 2^20: commit(a) + commit(b) == commit(a+b) via the device group law,
+    and commit of x*f against SRS == shifted MSM."""
+    n = 1 << 18
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    ctx.srs_generate(alpha, n)
+    a = synth.random_scalars(n, 1)
+    b = synth.random_scalars(n, 2)
+    ai, bi = synth.limbs_to_ints(a), synth.limbs_to_ints(b)
+    s = synth.ints_to_limbs([(x + y) % R for x, y in zip(ai, bi)])
+    ca, cb, cs = ctx.commit(a), ctx.commit(b), ctx.commit(s)
+    assert ctx.test_g1_op(0, [ca], [cb])[0] == cs
+    # opening identity: C - [y]G == [alpha - u] W   <=>  checked through scalars: f(alpha) - y == (alpha-u) q(alpha)
+    u = 77
+    y, w = ctx.open(a, u)
+    fa = synth.horner_mod_r(a, alpha)
+    k = (fa - y) * pow((alpha - u) % R, -1, R) % R
+    assert w == o.fast_mul(k)

@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py - KZG commit throughput (G1 MSM points/s) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port)
+
+Workload (BASELINE.json metric "KZG commits/sec and G1 MSM points/sec at degree
+2^20-2^24"): ONE step = one commit_kzg of a degree-(2^24 - 1) polynomial = one G1 MSM
+of 2^24 uniformly random scalars against the resident SRS [alpha^i]G, range-sharded
+over the N ranks (strong scaling; BASELINE config 4 at N = 8).  `value` is timed
+with the scalars already in HBM; `e2e` goes through the public API with host
+(pinned) scalars: H2D of the scalars and D2H of the commitment inside the timed
+region.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_IMAD_PER_POINT = 42240  # 16 windows x (8M+2S) x 264 IMAD (c = 16 canonical)
+IMAD_PER_MADD = 2640
+SORT_BYTES_PER_POINT = 672  # recode + sort phases
+
+
+def load_measured():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    imad = None
+    try:
+        imad = json.load(open(os.path.join(ROOT, "profiles", "imad_peak_r1.json")))
+    except Exception:
+        pass
+    return peaks, imad
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while a timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the oracle port (C restatement of the reference's naive algorithm) on the host
+# --------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c as oc
+    from myzkp_b200 import synth
+
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample
+    log2n = args.log2n
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    srs = oc.setup_kzg_bytes(alpha, sample, threads=threads)  # untimed fixture (kzg.rs:27-40)
+    coefs = synth.random_scalars(sample, synth.SEED_SCALARS + log2n).tobytes()
+    for _ in range(args.warmup):
+        oc.commit_kzg_bytes(coefs, srs, sample, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oc.commit_kzg_bytes(coefs, srs, sample, threads)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    t1 = time.perf_counter()
+    one = min(sample, 256)
+    oc.commit_kzg_bytes(coefs, srs, one, 1)
+    v1 = one / (time.perf_counter() - t1)
+    desc = (f"naive commit_kzg (affine double-and-add, ext-Euclid inversion per add; polynomial.rs:156-165) of the first "
+            f"{sample} coefficients of the 2^{log2n} workload per step, {threads} host threads splitting the index range "
+            f"(the reference itself is single-threaded: {v1:.0f} points/s on 1 core); reference is Rust and cannot be "
+            f"built in this image, so this is the C port oracle/oracle.c")
+    line = {
+        "impl": "reference", "metric": "g1_msm_points_per_sec", "value": val, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"kzg_commit_deg2^{log2n} (G1 MSM, 2^{log2n} BN128 points)", "sample_points": sample},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": desc,
+                         "value_1core": v1},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--log2n", type=int, default=24)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--no-verify", action="store_true", help="skip the O(N) host check of the full-size commitment")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--segment-len", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import myzkp_b200 as mz
+    from myzkp_b200 import synth
+    from myzkp_b200.dist import DeviceOps, ShardedKZG, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - myzkp_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = mz.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_msm_params(args.window_bits, args.segment_len)
+    log2n = args.log2n
+    n_total = 1 << log2n
+    lo, hi = shard_range(n_total, rank, world)
+    n_local = hi - lo
+
+    # ---- fixtures: SRS shard (resident) and scalars --------------------------------
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    t0 = time.perf_counter()
+    ctx.srs_generate(alpha, n_local, first=lo)
+    t_srs = time.perf_counter() - t0
+    scal_all = synth.random_scalars(n_total, synth.SEED_SCALARS + log2n)  # same on every rank
+    pinned = ctx.host_alloc(max(n_local, 1) * 32)
+    pinned[: n_local * 32] = scal_all[lo:hi].view(np.uint8).reshape(-1)
+    pinned_scal = pinned[: n_local * 32].reshape(n_local, 32)
+    d_scal = torch.empty(max(n_local, 1) * 4, dtype=torch.int64, device=dev)
+    d_scal[: n_local * 4].copy_(torch.from_numpy(pinned_scal.view(np.int64).reshape(-1)))
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    prover = ShardedKZG(DeviceOps(ctx, dev), rank, world, n_total)
+    pk = mz.PublicKeyKZG(ctx)
+
+    def step_resident():
+        prover.commit(d_scal.data_ptr(), out)
+
+    h2d_tensor = torch.from_numpy(pinned_scal.view(np.int64).reshape(-1))
+
+    def step_e2e():
+        if world == 1:
+            return mz.commit_kzg(mz.Polynomial(pinned_scal), pk)  # public API, host buffers
+        d_scal[: n_local * 4].copy_(h2d_tensor, non_blocking=True)
+        prover.commit(d_scal.data_ptr(), out)
+        return out.cpu()
+
+    # ---- correctness before timing ---------------------------------------------------
+    step_resident()
+    torch.cuda.synchronize()
+    got = mz.context.point_from_bytes(out.cpu().numpy().tobytes())
+    verified = None
+    if rank == 0 and not args.no_verify:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import myzkp_oracle as orc  # the checker only
+
+        fa = synth.horner_mod_r(scal_all, alpha)
+        verified = got == orc.fast_mul(fa)
+        if not verified:
+            raise SystemExit(f"bench.py: commitment mismatch vs oracle expected value at 2^{log2n}")
+
+    # ---- value: device-resident scalars ------------------------------------------------
+    ctx.enable_phase_timing(True)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0
+    phase_acc = {}
+    nph = min(args.steps, 32)
+    info = {}
+    for back in range(nph):
+        ph, info = ctx.msm_phases(back)
+        for k, v in ph.items():
+            phase_acc[k] = phase_acc.get(k, 0.0) + v / nph
+    ctx.enable_phase_timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n_total / (ms_step * 1e-3)
+
+    # ---- e2e: host scalars through the public API ----------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    e2e_val = n_total / (e2e_ms * 1e-3)
+    e2e_point = res.as_tuple() if world == 1 else mz.context.point_from_bytes(res.numpy().tobytes())
+    if e2e_point != got:
+        raise SystemExit("bench.py: e2e path disagrees with the device-resident path")
+
+    # ---- roofline of the dominant kernel (msm_accumulate) on this rank ------------------------
+    peaks, imad = load_measured()
+    imad_peak = (imad or {}).get("imad_peak_Tops")
+    acc_ms = phase_acc.get("accumulate", -1.0)
+    sort_ms = phase_acc.get("recode", 0.0) + phase_acc.get("sort", 0.0)
+    roofline = None
+    roofline_hbm = None
+    if acc_ms > 0:
+        achieved = n_local * ALG_IMAD_PER_POINT / (acc_ms * 1e-3) / 1e12
+        executed = info.get("entries", 0) * IMAD_PER_MADD / (acc_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic_r1.json"))).get(f"2^{log2n}_n{world}")
+        except Exception:
+            pass
+        roofline = {
+            "kernel": "msm_accumulate", "bound": "int32_imad", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD/s",
+            "frac": (achieved / imad_peak) if imad_peak else None, "traffic": traffic,
+            "peak_source": "measured (bench/imad_peak.cu on this pool's B200, profiles/imad_peak_r1.json)" if imad_peak else None,
+            "executed_TIMAD_s": executed, "executed_frac": (executed / imad_peak) if imad_peak else None,
+            "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step,
+            "note": "achieved = points x 42240 algorithmic IMAD (SURVEY 8d, c=16 XYZZ) / accumulate time; executed = "
+                    "entries x 2640 IMAD actually issued (window c=%d, %d windows)" % (info.get("window_bits", 0), info.get("windows", 0)),
+        }
+        if sort_ms > 0 and peaks.get("hbm_gbs"):
+            gbs = n_local * SORT_BYTES_PER_POINT / (sort_ms * 1e-3) / 1e9
+            roofline_hbm = {"kernels": "msm_recode + radix sort", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "phase_ms": sort_ms}
+
+    # ---- cpu baseline + extras (rank 0, N = 1) -----------------------------------------------
+    cpu_baseline = None
+    extra = {}
+    if rank == 0 and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_c as oc
+
+        sample = min(args.cpu_sample, n_total)
+        pts = ctx.srs_read(0, sample)
+        srs_bytes = b"".join(mz.context.point_to_bytes(p) for p in pts)
+        cb = scal_all[:sample].tobytes()
+        t0 = time.perf_counter()
+        cpu_pt = oc.commit_kzg_bytes(cb, srs_bytes, sample, 1)
+        dt = time.perf_counter() - t0
+        gpu_pt = ctx.commit(scal_all[:sample])
+        if cpu_pt != gpu_pt:
+            raise SystemExit("bench.py: GPU commit of the sample prefix differs from the oracle port")
+        cpu_baseline = {
+            "value": sample / dt, "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/oracle.c naive commit_kzg (reference algorithm, polynomial.rs:156-165) of the first {sample} "
+                      f"coefficients of this workload on 1 host core (the reference is single-threaded; host has "
+                      f"{os.cpu_count()} cores); result bit-identical to the GPU commit of the same prefix",
+            "seconds": dt,
+        }
+        if not args.no_extras:
+            extra = run_extras(ctx, mz, synth, torch, alpha, log2n)
+
+    if rank == 0:
+        line = {
+            "metric": "g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32x8 (254-bit modular integers, Montgomery)", "data": "synthetic",
+            "config": {
+                "workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
+                "points_total": n_total, "points_per_gpu": n_local, "parallelism": f"range-sharded x{world}",
+                "l2": "inputs larger than L2 (scalars %d MiB + SRS table %d MiB per GPU; no flush needed)"
+                      % (n_local * 32 >> 20, n_local * 64 * 32 >> 20),
+                "window_bits": info.get("window_bits"), "srs_setup_s": t_srs,
+            },
+            "commits_per_sec": 1e3 / ms_step,
+            "e2e": {"value": e2e_val, "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n_total * 32,
+                    "d2h_bytes_per_step": 64 * world},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
+            "phases_ms": phase_acc,
+            "cpu_baseline": cpu_baseline,
+            "verified_vs_oracle": verified,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(ctx, mz, synth, torch, alpha, log2n):
+    """Secondary BASELINE configs on one GPU (device events, scalars resident): reported, not the headline."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ex = {}
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    y = torch.zeros(32, dtype=torch.uint8, device=dev)
+    u = synth.random_scalar(synth.SEED_OPEN)
+    for lg in (16, 20):
+        if lg > log2n:
+            continue
+        n = 1 << lg
+        sc = torch.from_numpy(synth.random_scalars(n, synth.SEED_SCALARS + lg).view(np.int64).reshape(-1)).to(dev)
+        ms_c = timeit(lambda: ctx.commit_dev(sc.data_ptr(), n, out.data_ptr()))
+        ms_o = timeit(lambda: ctx.open_dev(sc.data_ptr(), n, u, y.data_ptr(), out.data_ptr()))
+        ex[f"commit_2^{lg}_ms"] = ms_c
+        ex[f"open_2^{lg}_ms"] = ms_o
+        ex[f"commit_2^{lg}_points_per_s"] = n / (ms_c * 1e-3)
+    if log2n >= 20:
+        n = 1 << 20
+        coefs = synth.random_scalars(n, synth.SEED_GEMINI_COEF)
+        rhos = synth.limbs_to_ints(synth.random_scalars(20, synth.SEED_GEMINI_RHO))
+        t0 = time.perf_counter()
+        ctx.gemini_fold_commit(coefs, rhos)
+        t0 = time.perf_counter()
+        ctx.gemini_fold_commit(coefs, rhos)
+        ex["gemini_2^20_fold_commit_21_polys_host_api_ms"] = (time.perf_counter() - t0) * 1e3
+    return ex
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,14 @@ uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
  * accumulate segment. */
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
 
+/* Per-phase CUDA-event timing of the MSM (events on the ctx stream, kept for the
+ * last 32 MSMs so a timed loop can be read back after its final sync).
+ * back = 0 is the most recent MSM.  out_ms = {recode, sort, accumulate, merge
+ * heads, bucket reduce + tree sum} in ms (-1 when timing was off); out_info =
+ * {window bits c, windows W, entries W*n, segment length, segments, buckets}. */
+int myzkp_ctx_enable_phase_timing(myzkp_ctx* ctx, int on);
+int myzkp_ctx_msm_phases(myzkp_ctx* ctx, int back, float out_ms[5], uint64_t out_info[6]);
+
 /* pinned host memory for callers that want DMA-able buffers */
 int myzkp_host_alloc(void** out, size_t bytes);
 int myzkp_host_free(void* p);

@@ -84,6 +84,34 @@ class Context:
     def set_msm_params(self, window_bits: int = 0, segment_len: int = 0):
         self._ck(self._lib.myzkp_ctx_set_msm_params(self.h, window_bits, segment_len))
 
+    def enable_phase_timing(self, on: bool = True):
+        self._ck(self._lib.myzkp_ctx_enable_phase_timing(self.h, 1 if on else 0))
+
+    def msm_phases(self, back: int = 0):
+        """({phase: ms}, info) of the MSM `back` calls ago (0 = last); syncs on its last event."""
+        ms = (ctypes.c_float * 5)()
+        info = (ctypes.c_uint64 * 6)()
+        self._ck(self._lib.myzkp_ctx_msm_phases(self.h, back, ms, info))
+        names = ("recode", "sort", "accumulate", "merge_heads", "bucket_reduce")
+        keys = ("window_bits", "windows", "entries", "segment_len", "segments", "buckets")
+        return {k: float(v) for k, v in zip(names, ms)}, {k: int(v) for k, v in zip(keys, info)}
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Pinned host buffer as a uint8 numpy array (freed with host_free)."""
+        p = ctypes.c_void_p()
+        code = self._lib.myzkp_host_alloc(ctypes.byref(p), nbytes)
+        if code != 0:
+            raise _lib.MyzkpError(code, "pinned allocation failed")
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = self._pinned.pop(arr.ctypes.data)
+        self._lib.myzkp_host_free(p)
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.myzkp_kernel_launches(self.h))

@@ -76,6 +76,9 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
                     &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->red_a, &ctx->red_b,
                     &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
   for (DevBuf* b : bufs) b->release();
+  for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
+    for (int i = 0; i < 6; i++)
+      if (ctx->phase_ev[s][i]) cudaEventDestroy(ctx->phase_ev[s][i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MYZKP_OK;
@@ -108,6 +111,30 @@ int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
   if (segment_len < 0 || segment_len > 65536) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bad segment_len");
   ctx->window_bits = window_bits;
   ctx->segment_len = segment_len;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_enable_phase_timing(myzkp_ctx* ctx, int on) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->phase_timing = on != 0;
+  if (on && !ctx->phase_ev[0][0])
+    for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
+      for (int i = 0; i < 6; i++) MZ_CUDA_TRY(ctx, cudaEventCreate(&ctx->phase_ev[s][i]));
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_msm_phases(myzkp_ctx* ctx, int back, float out_ms[5], uint64_t out_info[6]) {
+  if (!ctx || !out_ms || !out_info || back < 0 || back >= myzkp_ctx::kPhaseSlots) return MYZKP_ERR_INVALID_ARG;
+  if ((uint64_t)back >= ctx->msm_count) return fail(ctx, MYZKP_ERR_INVALID_ARG, "no such MSM recorded");
+  const int slot = (int)((ctx->msm_count - 1 - back) % myzkp_ctx::kPhaseSlots);
+  for (int i = 0; i < 6; i++) out_info[i] = ctx->msm_info[slot][i];
+  for (int i = 0; i < 5; i++) out_ms[i] = -1.f;
+  if (!ctx->phase_valid[slot]) return MYZKP_OK;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  MZ_CUDA_TRY(ctx, cudaEventSynchronize(ctx->phase_ev[slot][5]));
+  for (int i = 0; i < 5; i++)
+    MZ_CUDA_TRY(ctx, cudaEventElapsedTime(&out_ms[i], ctx->phase_ev[slot][i], ctx->phase_ev[slot][i + 1]));
   return MYZKP_OK;
 }
 

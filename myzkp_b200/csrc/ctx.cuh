@@ -74,8 +74,16 @@ struct myzkp_ctx {
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
   mz::DevBuf xyzz_tmp;     // XYZZ temporaries (SRS generation)
-  void* pinned = nullptr;  // pinned staging for small D2H results
-  size_t pinned_cap = 0;
+  // optional per-phase CUDA-event timing of the last MSM (bench.py roofline)
+  // phases: 0 recode, 1 sort, 2 accumulate, 3 merge heads, 4 bucket reduce + tree sum
+  // a ring of kPhaseSlots MSM calls so a timed loop can be read back after its final sync
+  static constexpr int kPhaseSlots = 32;
+  bool phase_timing = false;
+  cudaEvent_t phase_ev[kPhaseSlots][6] = {};
+  bool phase_valid[kPhaseSlots] = {};
+  uint64_t msm_count = 0;  // MSMs run so far (slot = count % kPhaseSlots)
+  // facts about each MSM: window bits, windows, entries, segment length, segments, buckets
+  uint64_t msm_info[kPhaseSlots][6] = {};
 };
 
 #define MZ_CUDA_TRY(ctx, expr)                                                        \

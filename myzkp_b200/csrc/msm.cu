@@ -292,11 +292,17 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   uint32_t* vals_a = ctx->vals_a.as<uint32_t>();
   uint32_t* vals_b = ctx->vals_b.as<uint32_t>();
 
+  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
+  const bool timing = ctx->phase_timing && ctx->phase_ev[0][0];
+#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][i], ctx->stream)); } while (0)
+  ctx->phase_valid[slot] = false;
+  MZ_PHASE(0);
   // 1. recode
   msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, (uint32_t)ctx->srs_n,
                                                                    (uint32_t)srs_off, keys_a, vals_a, flag);
   MZ_LAUNCH_CHECK(ctx);
 
+  MZ_PHASE(1);
   // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit)
   size_t tmp_bytes = 0;
   MZ_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, M, 0, c,
@@ -317,16 +323,19 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
   MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+  MZ_PHASE(2);
   msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
       keys_b, vals_b, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
       ctx->head_keys.as<uint32_t>(), T);
   MZ_LAUNCH_CHECK(ctx);
 
+  MZ_PHASE(3);
   // 4. merge segment heads
   msm_merge_heads<<<(unsigned)((T + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
                                                                         ctx->head_keys.as<uint32_t>(), T, nb);
   MZ_LAUNCH_CHECK(ctx);
 
+  MZ_PHASE(4);
   // 5. bucket reduce + tree sum
   uint32_t Lb = nb >= (1u << 20) ? 64 : 8;
   uint32_t nchunks = (nb + Lb - 1) / Lb;
@@ -336,6 +345,16 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
                                                                     ctx->red_a.as<XYZZ>());
   MZ_LAUNCH_CHECK(ctx);
   MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out));
+  MZ_PHASE(5);
+#undef MZ_PHASE
+  ctx->phase_valid[slot] = timing;
+  ctx->msm_info[slot][0] = (uint64_t)c;
+  ctx->msm_info[slot][1] = (uint64_t)W;
+  ctx->msm_info[slot][2] = M;
+  ctx->msm_info[slot][3] = L;
+  ctx->msm_info[slot][4] = T;
+  ctx->msm_info[slot][5] = nb;
+  ctx->msm_count++;
   return MYZKP_OK;
 }
 

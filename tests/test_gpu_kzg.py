@@ -185,3 +185,55 @@ def test_linearity_and_shift_properties_full_size(ctx):
     fa = synth.horner_mod_r(a, alpha)
     k = (fa - y) * pow((alpha - u) % R, -1, R) % R
     assert w == o.fast_mul(k)
+
+
+def test_sharded_commit_and_open_emulated_ranks(ctx):
+    """The multi-GPU path on one GPU: one Context per emulated rank, each with its SRS range
+    (srs_generate first=lo), partial XYZZ per rank, sum_partials; open through range_eval /
+    compose_carries / range_quotient - everything but the NCCL all-gather itself."""
+    import torch
+
+    from myzkp_b200.dist import compose_carries, shard_range
+
+    n, world = 3001, 3
+    alpha, u = 0x1234567890ABCDEF1234567, 0xFEDCBA987654321
+    coefs = synth.random_scalars(n, 7)
+    ints = synth.limbs_to_ints(coefs)
+    dev = torch.device("cuda", 0)
+    d_all = torch.from_numpy(coefs.view(np.int64).reshape(-1)).to(dev)
+    ranks = []
+    for r in range(world):
+        c = mz.Context(0)
+        lo, hi = shard_range(n, r, world)
+        c.srs_generate(alpha, hi - lo, first=lo)
+        assert c.srs_read(0, 1)[0] == o.fast_mul(pow(alpha, lo, R))
+        ranks.append((c, lo, hi))
+    partials = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
+    pairs = torch.zeros(world * 64, dtype=torch.uint8, device=dev)
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    for r, (c, lo, hi) in enumerate(ranks):
+        c.msm_partial_dev(d_all.data_ptr() + lo * 32, hi - lo, 0, partials.data_ptr() + 128 * r)
+        c.fr_range_eval_dev(d_all.data_ptr() + lo * 32, hi - lo, u, pairs.data_ptr() + 64 * r, pairs.data_ptr() + 64 * r + 32)
+        c.sync()
+    ranks[0][0].sum_partials_dev(partials.data_ptr(), world, out.data_ptr())
+    ranks[0][0].sync()
+    assert mz.context.point_from_bytes(out.cpu().numpy().tobytes()) == o.expected_commit(ints, alpha)
+    raw = pairs.cpu().numpy().tobytes()
+    hs = [int.from_bytes(raw[64 * r : 64 * r + 32], "little") for r in range(world)]
+    ms = [int.from_bytes(raw[64 * r + 32 : 64 * r + 64], "little") for r in range(world)]
+    for r, (c, lo, hi) in enumerate(ranks):
+        assert ms[r] == pow(u, hi - lo, R)
+    carries = compose_carries(hs, ms)
+    c0s = torch.zeros(world * 32, dtype=torch.uint8, device=dev)
+    qs = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
+    for r, (c, lo, hi) in enumerate(ranks):
+        c.fr_range_quotient_dev(d_all.data_ptr() + lo * 32, hi - lo, u, carries[r], qs.data_ptr() + lo * 32, c0s.data_ptr() + 32 * r)
+        c.msm_partial_dev(qs.data_ptr() + lo * 32, hi - lo, 0, partials.data_ptr() + 128 * r)
+        c.sync()
+    ranks[1][0].sum_partials_dev(partials.data_ptr(), world, out.data_ptr())
+    ranks[1][0].sync()
+    ey, ew = o.expected_open(ints, u, alpha)
+    assert int.from_bytes(c0s.cpu().numpy().tobytes()[:32], "little") == ey
+    assert mz.context.point_from_bytes(out.cpu().numpy().tobytes()) == ew
+    for c, _, _ in ranks:
+        c.close()

@@ -1,0 +1,81 @@
+// Header-only C++ mirror of the reference's KZG surface over the C ABI (include/myzkp_b200.h):
+// setup_kzg / commit_kzg / open_kzg / commit_gemini (myzkp/src/modules/algebra/kzg.rs:27-72,
+// gemini.rs:112-114) with the same argument meaning and error behaviour (errors throw where the
+// reference panics).  Scalars and coordinates are 32-byte little-endian canonical values.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "myzkp_b200.h"
+
+namespace myzkp_b200 {
+
+using Scalar = std::array<uint8_t, 32>;  // FqOrder value, canonical, LE
+struct G1Point {                         // EllipticCurvePoint<Fq, BN128Curve> (curve.rs:17-22)
+  std::array<uint8_t, 64> xy{};          // x || y; all-zero = point at infinity
+  bool is_point_at_infinity() const {
+    for (uint8_t b : xy) if (b) return false;
+    return true;
+  }
+  bool operator==(const G1Point& o) const { return xy == o.xy; }
+};
+struct Polynomial {                      // Polynomial<FqOrder> (polynomial.rs:69-74), low -> high degree
+  std::vector<Scalar> coef;
+};
+struct ProofKZG {                        // kzg.rs:15-18
+  Scalar y{};
+  G1Point w;
+};
+using CommitmentKZG = G1Point;
+
+class PublicKeyKZG {                     // kzg.rs:8-11; powers_1 resident on the GPU
+ public:
+  explicit PublicKeyKZG(int device = 0) {
+    if (myzkp_ctx_create(&ctx_, device) != MYZKP_OK) throw std::runtime_error("myzkp_b200: no usable CUDA device (no CPU fallback)");
+  }
+  ~PublicKeyKZG() { myzkp_ctx_destroy(ctx_); }
+  PublicKeyKZG(const PublicKeyKZG&) = delete;
+  PublicKeyKZG& operator=(const PublicKeyKZG&) = delete;
+  myzkp_ctx* ctx() const { return ctx_; }
+  size_t size() const { return myzkp_srs_len(ctx_); }
+  std::vector<G1Point> powers_1() const {
+    std::vector<G1Point> out(size());
+    check(myzkp_srs_read_g1(ctx_, 0, out.size(), out.empty() ? nullptr : out[0].xy.data()));
+    return out;
+  }
+  void check(int code) const {
+    if (code != MYZKP_OK) throw std::runtime_error(std::string("myzkp_b200: ") + myzkp_last_error(ctx_));
+  }
+
+ private:
+  myzkp_ctx* ctx_ = nullptr;
+};
+
+// setup_kzg (kzg.rs:27-40) with alpha injected; max_d + 1 powers of the standard generator
+inline void setup_kzg(PublicKeyKZG& pk, size_t max_d, const Scalar& alpha) {
+  pk.check(myzkp_srs_generate_g1(pk.ctx(), alpha.data(), 0, max_d + 1));
+}
+// commit_kzg (kzg.rs:57-59)
+inline CommitmentKZG commit_kzg(const Polynomial& f, const PublicKeyKZG& pk) {
+  G1Point c;
+  pk.check(myzkp_kzg_commit(pk.ctx(), f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(), c.xy.data()));
+  return c;
+}
+// open_kzg (kzg.rs:61-72)
+inline ProofKZG open_kzg(const Polynomial& f, const Scalar& u, const PublicKeyKZG& pk) {
+  ProofKZG p;
+  pk.check(myzkp_kzg_open(pk.ctx(), f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(), u.data(), p.y.data(),
+                          p.w.xy.data()));
+  return p;
+}
+// commit_gemini (gemini.rs:112-114)
+inline std::vector<CommitmentKZG> commit_gemini(const std::vector<Polynomial>& polys, const PublicKeyKZG& pk) {
+  std::vector<CommitmentKZG> out;
+  for (const auto& p : polys) out.push_back(commit_kzg(p, pk));
+  return out;
+}
+
+}  // namespace myzkp_b200

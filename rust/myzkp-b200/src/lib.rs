@@ -1,0 +1,104 @@
+//! Safe wrapper that keeps the reference's KZG surface
+//! (myzkp/src/modules/algebra/kzg.rs:27-72, gemini.rs:112-114) and moves the work to the GPU.
+//!
+//! Marshalling follows the reference's only host<->device precedent,
+//! myzkp/examples/sumcheck/src/utils.rs:51-72: canonical value -> to_u64_digits -> 32 bytes LE.
+use std::ffi::CStr;
+use std::ptr;
+
+use myzkp::modules::algebra::curve::bn128::{Fq, FqOrder, G1Point, G2Point, BN128};
+use myzkp::modules::algebra::field::Field;
+use myzkp::modules::algebra::polynomial::Polynomial;
+use myzkp::modules::algebra::ring::Ring;
+use myzkp_b200_sys as sys;
+use num_bigint::{BigInt, Sign};
+
+pub type CommitmentKZG = G1Point;
+
+pub struct ProofKZG {
+    pub y: FqOrder,
+    pub w: G1Point,
+}
+
+/// PublicKeyKZG whose powers_1 live on the GPU as the resident SRS table (kzg.rs:8-11).
+pub struct GpuPublicKeyKZG {
+    ctx: *mut sys::myzkp_ctx,
+    pub powers_2: Vec<G2Point>,
+}
+
+impl Drop for GpuPublicKeyKZG {
+    fn drop(&mut self) {
+        unsafe { sys::myzkp_ctx_destroy(self.ctx) };
+    }
+}
+
+fn check(ctx: *mut sys::myzkp_ctx, code: i32) {
+    if code != sys::MYZKP_OK {
+        let msg = unsafe { CStr::from_ptr(sys::myzkp_last_error(ctx)) }.to_string_lossy().into_owned();
+        // the reference panics in the corresponding situations (e.g. polynomial.rs:162)
+        panic!("myzkp_b200 error {}: {}", code, msg);
+    }
+}
+
+fn scalar_to_le(x: &FqOrder) -> [u8; 32] {
+    let (_, digits) = x.sanitize().get_value().to_u64_digits(); // polynomial.rs:162 sanitizes before the MSM
+    let mut out = [0u8; 32];
+    for (i, d) in digits.iter().take(4).enumerate() {
+        out[8 * i..8 * i + 8].copy_from_slice(&d.to_le_bytes());
+    }
+    out
+}
+
+fn marshal_scalars(coef: &[FqOrder]) -> Vec<u8> {
+    let mut v = Vec::with_capacity(32 * coef.len());
+    for c in coef {
+        v.extend_from_slice(&scalar_to_le(c));
+    }
+    v
+}
+
+fn point_from_bytes(b: &[u8; 64]) -> G1Point {
+    if b.iter().all(|&x| x == 0) {
+        return G1Point::point_at_infinity(); // curve.rs:34-39
+    }
+    let x = BigInt::from_bytes_le(Sign::Plus, &b[..32]);
+    let y = BigInt::from_bytes_le(Sign::Plus, &b[32..]);
+    G1Point::new(Fq::from_value(x), Fq::from_value(y))
+}
+
+/// setup_kzg (kzg.rs:27-40).  `g1` must be BN128::generator_g1(); alpha is drawn like the reference does.
+pub fn setup_kzg(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPublicKeyKZG {
+    assert!(*g1 == BN128::generator_g1());
+    let alpha = FqOrder::random_element(&[]); // kzg.rs:28
+    let mut ctx = ptr::null_mut();
+    let code = unsafe { sys::myzkp_ctx_create(&mut ctx, 0) };
+    assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
+    let a = scalar_to_le(&alpha);
+    check(ctx, unsafe { sys::myzkp_srs_generate_g1(ctx, a.as_ptr(), 0, max_d + 1) });
+    let powers_2 = vec![g2.clone(), g2.mul_ref(alpha.get_value())]; // kzg.rs:37 (CPU, verifier side)
+    GpuPublicKeyKZG { ctx, powers_2 }
+}
+
+/// commit_kzg (kzg.rs:57-59)
+pub fn commit_kzg(f: &Polynomial<FqOrder>, pk: &GpuPublicKeyKZG) -> CommitmentKZG {
+    let bytes = marshal_scalars(&f.coef);
+    let mut out = [0u8; 64];
+    check(pk.ctx, unsafe { sys::myzkp_kzg_commit(pk.ctx, bytes.as_ptr(), f.coef.len(), out.as_mut_ptr()) });
+    point_from_bytes(&out)
+}
+
+/// open_kzg (kzg.rs:61-72)
+pub fn open_kzg(f: &Polynomial<FqOrder>, u: &FqOrder, pk: &GpuPublicKeyKZG) -> ProofKZG {
+    let bytes = marshal_scalars(&f.coef);
+    let ub = scalar_to_le(u);
+    let (mut y, mut w) = ([0u8; 32], [0u8; 64]);
+    check(pk.ctx, unsafe {
+        sys::myzkp_kzg_open(pk.ctx, bytes.as_ptr(), f.coef.len(), ub.as_ptr(), y.as_mut_ptr(), w.as_mut_ptr())
+    });
+    ProofKZG { y: FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, &y)), w: point_from_bytes(&w) }
+}
+
+/// commit_gemini (gemini.rs:112-114)
+pub fn commit_gemini(polys: &[Polynomial<FqOrder>], pk: &GpuPublicKeyKZG) -> Vec<CommitmentKZG> {
+    polys.iter().map(|p| commit_kzg(p, pk)).collect()
+}

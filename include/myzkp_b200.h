@@ -47,8 +47,9 @@ int myzkp_ctx_sync(myzkp_ctx* ctx);
 const char* myzkp_last_error(const myzkp_ctx* ctx);
 /* Number of this library's kernels launched by the ctx so far. */
 uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
-/* MSM tuning knobs (0 = automatic): window bits c in {8,16,24}; entries per
- * accumulate segment. */
+/* MSM tuning knobs (0 = automatic): window bits c, a multiple of the table stride
+ * (4, or 8 for very large SRS) up to 24 - other values fall back to automatic;
+ * entries per accumulate segment. */
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
 
 /* Per-phase CUDA-event timing of the MSM (events on the ctx stream, kept for the

@@ -106,8 +106,8 @@ uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx) { return ctx ? ctx->launche
 
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
   if (!ctx) return MYZKP_ERR_INVALID_ARG;
-  if (window_bits != 0 && window_bits != 8 && window_bits != 16 && window_bits != 24)
-    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window_bits must be 0, 8, 16 or 24");
+  if (window_bits < 0 || window_bits > 24 || window_bits % 4 != 0)
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window_bits must be 0 (auto) or a multiple of 4 up to 24");
   if (segment_len < 0 || segment_len > 65536) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bad segment_len");
   ctx->window_bits = window_bits;
   ctx->segment_len = segment_len;

@@ -10,11 +10,11 @@
 
 namespace mz {
 
-// Rows of the resident SRS table: row j holds 2^(8j) * P_i for every SRS point,
-// so that an MSM with window c (a multiple of 8) needs no doublings at all:
-// sum_w 2^(c w) d_w P = sum_w d_w * row[(c/8) w].
-constexpr int kTableStrideBits = 8;
-constexpr int kTableRows = 32;  // 8 * 32 = 256 >= 255 bits (254-bit scalar + sign carry)
+// Rows of the resident SRS table: row j holds 2^(s j) * P_i for every SRS point
+// (s = table stride bits), so that an MSM with window c (a multiple of s) needs no
+// doublings at all: sum_w 2^(c w) d_w P = sum_w d_w * row[(c/s) w].
+// s = 4 -> 64 rows (c in {4,8,...,24}); s = 8 -> 32 rows (c in {8,16,24}) for very large SRS.
+constexpr int kMaxTableRows = 64;  // s * rows = 256 >= 255 bits (254-bit scalar + sign carry)
 
 struct DevBuf {
   void* p = nullptr;
@@ -57,9 +57,11 @@ struct myzkp_ctx {
   int window_bits = 0;
   int segment_len = 0;
 
-  // resident SRS table: kTableRows rows of srs_n affine points (Montgomery)
+  // resident SRS table: table_rows rows of srs_n affine points (Montgomery)
   mz::Affine* table = nullptr;
   size_t srs_n = 0;
+  int table_stride = 4;  // bits between consecutive rows
+  int table_rows = 64;
 
   // fixed-base comb table of G for srs_generate: [32][256] affine
   mz::Affine* gcomb = nullptr;

@@ -41,6 +41,9 @@ MZ_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("subc.cc.u32 
 MZ_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; MZ_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 MZ_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 MZ_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+MZ_D void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+  MZ_ASM("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
 MZ_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MZ_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MZ_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MZ_ASM("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -67,6 +70,11 @@ inline uint32_t subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, tru
 inline uint32_t subc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, false); }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+  uint64_t t = (uint64_t)a * b;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+}
 inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, 0, true); }
 inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, g_cf, true); }
 inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, 0, true); }
@@ -262,10 +270,8 @@ MZ_HD void mont_row(uint32_t* E, uint32_t* O, const ArrAcc& a, uint32_t bi, bool
   if (first) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      O[j] = mul_lo(a(j + 1), bi);
-      O[j + 1] = mul_hi(a(j + 1), bi);
-      E[j] = mul_lo(a(j), bi);
-      E[j + 1] = mul_hi(a(j), bi);
+      mul_wide(a(j + 1), bi, O[j], O[j + 1]);
+      mul_wide(a(j), bi, E[j], E[j + 1]);
     }
   } else {
     // E is the previous row's odd array (already in place); O is the previous

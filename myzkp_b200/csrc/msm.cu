@@ -61,7 +61,8 @@ __device__ __forceinline__ XYZZ load_xyzz(const XYZZ* p) {
 // key = |d| - 1 in [0, 2^(c-1)), or `sentinel` = 2^(c-1) for d == 0 (sorted to
 // the end and ignored).  val = sign << 31 | (row(w) * srs_n + srs_off + i).
 __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ scalars, size_t n, int c, int W,
-                                                  uint32_t srs_n, uint32_t srs_off, uint32_t* __restrict__ keys,
+                                                  int stride_bits, uint32_t srs_n, uint32_t srs_off,
+                                                  uint32_t* __restrict__ keys,
                                                   uint32_t* __restrict__ vals, int* __restrict__ flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ s
   if (!fe_is_canonical(sc)) atomicOr(flag, 1);
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
-  const uint32_t rows_per_window = (uint32_t)(c / kTableStrideBits);
+  const uint32_t rows_per_window = (uint32_t)(c / stride_bits);
   uint32_t carry = 0;
   for (int w = 0; w < W; w++) {
     int bit = w * c;
@@ -243,11 +244,25 @@ __global__ void xyzz_set_inf(XYZZ* out) { store_xyzz(out, xyzz_inf()); }
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
+// Window choice by a cost model fitted to measurements on B200 (profiles/phase_sweep_r1.json):
+// accumulate 0.161 ns per entry, radix sort 0.0067 ns per entry per 8-bit pass, bucket
+// reduce max(0.35 ms latency floor, ~0.74..1.9 ns per bucket).
 static int pick_window(const myzkp_ctx* ctx, size_t n) {
-  if (ctx->window_bits == 8 || ctx->window_bits == 16 || ctx->window_bits == 24) return ctx->window_bits;
-  if (n < ((size_t)1 << 11)) return 8;
-  if (n >= ((size_t)1 << 23)) return 24;
-  return 16;
+  const int s = ctx->table_stride;
+  if (ctx->window_bits >= s && ctx->window_bits <= 24 && ctx->window_bits % s == 0) return ctx->window_bits;
+  int best = s;
+  double best_t = 1e300;
+  for (int c = s; c <= 24; c += s) {
+    if (c < 8 && n > 64) continue;
+    const double W = (255 + c - 1) / c;
+    const double entries = W * (double)n;
+    const double nb = (double)(1u << (c - 1));
+    double reduce = nb * (nb >= (double)(1u << 22) ? 0.74 : 1.95);
+    if (reduce < 350000.0) reduce = 350000.0 * (c >= 16 ? 1.0 : 0.6);
+    double t = entries * (0.161 + 0.0067 * ((c + 7) / 8)) + reduce;
+    if (t < best_t) { best_t = t; best = c; }
+  }
+  return best;
 }
 
 // tree-sum `count` XYZZ values living in buffer `a` (ping-pong with `b`); the
@@ -298,8 +313,9 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   ctx->phase_valid[slot] = false;
   MZ_PHASE(0);
   // 1. recode
-  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, (uint32_t)ctx->srs_n,
-                                                                   (uint32_t)srs_off, keys_a, vals_a, flag);
+  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, ctx->table_stride,
+                                                                   (uint32_t)ctx->srs_n, (uint32_t)srs_off, keys_a,
+                                                                   vals_a, flag);
   MZ_LAUNCH_CHECK(ctx);
 
   MZ_PHASE(1);
@@ -313,10 +329,15 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   ctx->launches += (c + 7) / 8 + 2;  // onesweep: histogram + scan + one kernel per 8-bit pass
 
   // 3. accumulate
+  // Segment length: enough segments to fill the GPU several times over, but not much
+  // shorter than the average bucket run - every extra segment inside a run costs a
+  // head that msm_merge_heads must fold in serially.
   uint32_t L = (uint32_t)ctx->segment_len;
   if (L == 0) {
     uint64_t target_threads = (uint64_t)ctx->sm_count * 512 * 8;
     uint64_t l = (M + target_threads - 1) / target_threads;
+    uint64_t avg_run = M / nb;
+    if (l < avg_run / 2) l = avg_run / 2;
     L = (uint32_t)(l < 8 ? 8 : (l > 256 ? 256 : l));
   }
   const uint64_t T = (M + L - 1) / L;
@@ -337,7 +358,7 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 
   MZ_PHASE(4);
   // 5. bucket reduce + tree sum
-  uint32_t Lb = nb >= (1u << 20) ? 64 : 8;
+  uint32_t Lb = nb >= (1u << 22) ? 64 : (nb >= (1u << 20) ? 16 : 8);
   uint32_t nchunks = (nb + Lb - 1) / Lb;
   MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));

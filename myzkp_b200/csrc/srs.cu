@@ -45,7 +45,7 @@ __global__ void srs_export(const Affine* row0, size_t n, uint32_t* out) {
 }
 
 // rows 1..rows-1 from row 0: Jacobian doubling chain, one batched inversion per point
-__global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int rows) {
+__global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int rows, int stride_bits) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine p = tbl[i];
@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int
   }
   Jac cur;
   cur.x = p.x; cur.y = p.y; cur.z = Fq::one();
-  Fq zs[kTableRows - 1];
-  Fq pref[kTableRows - 1];
+  Fq zs[kMaxTableRows - 1];
+  Fq pref[kMaxTableRows - 1];
   for (int j = 1; j < rows; j++) {
 #pragma unroll 1
-    for (int d = 0; d < kTableStrideBits; d++) jac_dbl(cur);
+    for (int d = 0; d < stride_bits; d++) jac_dbl(cur);
     Affine un;  // unnormalised X, Y parked in the table slot
     un.x = cur.x; un.y = cur.y;
     tbl[(size_t)j * n + i] = un;
@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(128) batch_to_affine(const XYZZ* in, size_t n,
 }
 
 // comb[j*256 + d] = d * base2[j]  (base2[j] = 2^(8j) G, affine), d = 0..255 as XYZZ
+constexpr int kCombRows = 32;
 __global__ void srs_comb_multiples(const Affine* base2, XYZZ* out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= kTableRows * 256) return;
+  if (idx >= kCombRows * 256) return;
   int j = idx >> 8, d = idx & 255;
   Affine b = base2[j];
   XYZZ acc = xyzz_inf();
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(128) srs_fixed_base(const uint32_t* scalars, s
   for (int k = 0; k < 8; k++) s[k] = scalars[i * 8 + k];
   XYZZ acc = xyzz_inf();
 #pragma unroll 1
-  for (int j = 0; j < kTableRows; j++) {
+  for (int j = 0; j < kCombRows; j++) {
     uint32_t d = (s[j >> 2] >> ((j & 3) * 8)) & 255u;
     if (d) xyzz_madd(acc, comb[j * 256 + d]);
   }
@@ -170,8 +171,17 @@ int srs_alloc(myzkp_ctx* ctx, size_t n) {
     ctx->srs_n = 0;
   }
   if (n == 0) return MYZKP_OK;
-  if ((uint64_t)n * kTableRows >= (1ull << 31)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "SRS too large (n * 32 must be < 2^31)");
-  MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->table, n * kTableRows * sizeof(Affine)));
+  // stride 4 (64 rows) when the table fits comfortably, else stride 8 (32 rows)
+  size_t free_b = 0, total_b = 0;
+  MZ_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+  ctx->table_stride = 4;
+  ctx->table_rows = 64;
+  if ((uint64_t)n * 64 >= (1ull << 31) || (double)n * 64 * sizeof(Affine) > 0.55 * (double)free_b) {
+    ctx->table_stride = 8;
+    ctx->table_rows = 32;
+  }
+  if ((uint64_t)n * ctx->table_rows >= (1ull << 31)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "SRS too large (n * rows must be < 2^31)");
+  MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->table, n * ctx->table_rows * sizeof(Affine)));
   ctx->srs_n = n;
   return MYZKP_OK;
 }
@@ -179,7 +189,7 @@ int srs_alloc(myzkp_ctx* ctx, size_t n) {
 int srs_build_from_row0(myzkp_ctx* ctx) {
   size_t n = ctx->srs_n;
   if (n == 0) return MYZKP_OK;
-  srs_build_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->table, n, kTableRows);
+  srs_build_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->table, n, ctx->table_rows, ctx->table_stride);
   MZ_LAUNCH_CHECK(ctx);
   return MYZKP_OK;
 }
@@ -188,12 +198,12 @@ static int ensure_gcomb(myzkp_ctx* ctx) {
   if (ctx->gcomb) return MYZKP_OK;
   // base2[j] = 2^(8j) G through the same row builder (n = 1)
   Affine* base2 = nullptr;
-  MZ_CUDA_TRY(ctx, cudaMalloc(&base2, kTableRows * sizeof(Affine)));
+  MZ_CUDA_TRY(ctx, cudaMalloc(&base2, kCombRows * sizeof(Affine)));
   srs_set_generator<<<1, 1, 0, ctx->stream>>>(base2);
   MZ_LAUNCH_CHECK(ctx);
-  srs_build_rows<<<1, 128, 0, ctx->stream>>>(base2, 1, kTableRows);
+  srs_build_rows<<<1, 128, 0, ctx->stream>>>(base2, 1, kCombRows, 8);
   MZ_LAUNCH_CHECK(ctx);
-  const int total = kTableRows * 256;
+  const int total = kCombRows * 256;
   MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((size_t)total * sizeof(XYZZ)));
   srs_comb_multiples<<<(total + 127) / 128, 128, 0, ctx->stream>>>(base2, ctx->xyzz_tmp.as<XYZZ>());
   MZ_LAUNCH_CHECK(ctx);

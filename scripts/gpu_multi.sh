@@ -1,0 +1,8 @@
+#!/bin/bash
+# multi-GPU session: bench at N GPUs through torchrun (NCCL), N from $1
+N=${1:-2}
+mkdir -p gpurun_out
+nvidia-smi -L | head -8
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+   bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json

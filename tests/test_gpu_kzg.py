@@ -103,7 +103,7 @@ def test_window_sizes_and_segments_agree(ctx):
     ctx.srs_generate(alpha, n)
     exp = o.expected_commit(ints, alpha)
     try:
-        for c in (8, 16, 24):
+        for c in (4, 8, 12, 16, 20, 24):
             for seg in (0, 1, 7, 1000):
                 ctx.set_msm_params(c, seg)
                 assert ctx.commit(coefs) == exp, (c, seg)
@@ -129,7 +129,7 @@ def test_scalar_distributions(ctx):
     }
     for name, sc in dists.items():
         exp = o.expected_commit(sc, alpha)
-        for c in (8, 16, 24):
+        for c in (4, 8, 12, 16, 20, 24):
             ctx.set_msm_params(c, 0)
             assert ctx.commit(sc) == exp, (name, c)
     ctx.set_msm_params(0, 0)

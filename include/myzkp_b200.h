@@ -47,10 +47,16 @@ int myzkp_ctx_sync(myzkp_ctx* ctx);
 const char* myzkp_last_error(const myzkp_ctx* ctx);
 /* Number of this library's kernels launched by the ctx so far. */
 uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
-/* MSM tuning knobs (0 = automatic): window bits c, a multiple of the table stride
- * (4, or 8 for very large SRS) up to 24 - other values fall back to automatic;
- * entries per accumulate segment. */
+/* MSM tuning knobs (0 = automatic): window bits c out of the windows the resident
+ * table supports (4, 8, 12, 16, 20, 22, 24; or 8, 16, 24 for a very large SRS) -
+ * other values fall back to automatic; entries per accumulate segment. */
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
+
+/* Host-buffer commit/open upload a large polynomial in chunks on a copy stream while
+ * earlier chunks are already being processed (each chunk is an MSM against its own SRS
+ * range; the partial points are summed).  0 = automatic (1 below 2^23 coefficients,
+ * 2 at 2^23, 4 from 2^24), 1..8 forces a chunk count. */
+int myzkp_ctx_set_upload_chunks(myzkp_ctx* ctx, int chunks);
 
 /* Per-phase CUDA-event timing of the MSM (events on the ctx stream, kept for the
  * last 32 MSMs so a timed loop can be read back after its final sync).

@@ -84,6 +84,9 @@ class Context:
     def set_msm_params(self, window_bits: int = 0, segment_len: int = 0):
         self._ck(self._lib.myzkp_ctx_set_msm_params(self.h, window_bits, segment_len))
 
+    def set_upload_chunks(self, chunks: int = 0):
+        self._ck(self._lib.myzkp_ctx_set_upload_chunks(self.h, chunks))
+
     def enable_phase_timing(self, on: bool = True):
         self._ck(self._lib.myzkp_ctx_enable_phase_timing(self.h, 1 if on else 0))
 

@@ -34,6 +34,37 @@ int begin_call(myzkp_ctx* ctx) {
   return MYZKP_OK;
 }
 
+// Upload pipeline for the host-buffer entry points: how many chunks to split n into
+int upload_chunks(const myzkp_ctx* ctx, size_t n) {
+  if (ctx->upload_chunks > 0) return (size_t)ctx->upload_chunks <= (n ? n : 1) ? ctx->upload_chunks : 1;
+  if (n >= ((size_t)1 << 24)) return 4;
+  if (n >= ((size_t)1 << 23)) return 2;
+  return 1;
+}
+int ensure_copy_stream(myzkp_ctx* ctx) {
+  if (ctx->copy_stream) return MYZKP_OK;
+  MZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+  MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->copy_done_ev, cudaEventDisableTiming));
+  return MYZKP_OK;
+}
+// enqueue the H2D copies of K contiguous chunks on the copy stream (chunk order given by `descending`)
+int enqueue_chunk_uploads(myzkp_ctx* ctx, const uint8_t* host, uint8_t* dev, size_t n, int K, bool descending) {
+  MZ_TRY(ensure_copy_stream(ctx));
+  // the copy stream must not overwrite the staging buffer while earlier work on `stream` still reads it
+  MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done_ev, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done_ev, 0));
+  const size_t per = (n + K - 1) / K;
+  for (int i = 0; i < K; i++) {
+    int k = descending ? K - 1 - i : i;
+    size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+    if (lo >= hi) { MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream)); continue; }
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(dev + lo * 32, host + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+  }
+  return MYZKP_OK;
+}
+
 int end_call_check_flag(myzkp_ctx* ctx) {
   int h_flag = 0;
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, ctx->small.as<uint8_t>() + kSmallFlag, sizeof(int), cudaMemcpyDeviceToHost,
@@ -72,6 +103,8 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->table) cudaFree(ctx->table);
   if (ctx->gcomb) cudaFree(ctx->gcomb);
+  if (ctx->d_row_of_bit) cudaFree(ctx->d_row_of_bit);
+  if (ctx->d_row_bits) cudaFree(ctx->d_row_bits);
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                     &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->red_a, &ctx->red_b,
                     &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
@@ -79,6 +112,10 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
     for (int i = 0; i < 6; i++)
       if (ctx->phase_ev[s][i]) cudaEventDestroy(ctx->phase_ev[s][i]);
+  for (int i = 0; i < 8; i++)
+    if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  if (ctx->copy_done_ev) cudaEventDestroy(ctx->copy_done_ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MYZKP_OK;
@@ -106,11 +143,17 @@ uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx) { return ctx ? ctx->launche
 
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
   if (!ctx) return MYZKP_ERR_INVALID_ARG;
-  if (window_bits < 0 || window_bits > 24 || window_bits % 4 != 0)
-    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window_bits must be 0 (auto) or a multiple of 4 up to 24");
+  if (window_bits < 0 || window_bits > 24)
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window_bits must be 0 (auto) or one of the supported windows (<= 24)");
   if (segment_len < 0 || segment_len > 65536) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bad segment_len");
   ctx->window_bits = window_bits;
   ctx->segment_len = segment_len;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_set_upload_chunks(myzkp_ctx* ctx, int chunks) {
+  if (!ctx || chunks < 0 || chunks > 8) return MYZKP_ERR_INVALID_ARG;
+  ctx->upload_chunks = chunks;
   return MYZKP_OK;
 }
 
@@ -215,11 +258,23 @@ int myzkp_kzg_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, uint8_t 
                                   "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
   MZ_TRY(begin_call(ctx));
   uint8_t* s = ctx->small.as<uint8_t>();
-  if (n) {
-    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
-    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const int K = upload_chunks(ctx, n);
+  if (n) MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+  if (K == 1) {
+    if (n) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MZ_TRY(myzkp_kzg_commit_dev(ctx, ctx->scalars.p, n, s + kSmallPoint));
+  } else {
+    // chunk k is committed (against SRS points [lo_k, hi_k)) while chunk k+1 is still on the bus
+    MZ_TRY(enqueue_chunk_uploads(ctx, coefs_le, ctx->scalars.as<uint8_t>(), n, K, false));
+    XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
+    const size_t per = (n + K - 1) / K;
+    for (int k = 0; k < K; k++) {
+      size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+      MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+      MZ_TRY(msm_xyzz(ctx, ctx->scalars.as<uint32_t>() + lo * 8, hi > lo ? hi - lo : 0, lo, res + k));
+    }
+    MZ_TRY(sum_partials(ctx, res, (size_t)K, s + kSmallPoint));
   }
-  MZ_TRY(myzkp_kzg_commit_dev(ctx, ctx->scalars.p, n, s + kSmallPoint));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_c, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
   return end_call_check_flag(ctx);
 }
@@ -229,13 +284,39 @@ int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint
   if (!ctx || (!coefs_le && n) || !u_le || !out_y || !out_w) return MYZKP_ERR_INVALID_ARG;
   if (n > ctx->srs_n + 1 || (n > 1 && !ctx->table))
     return fail(ctx, !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG, "quotient longer than the SRS");
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
   MZ_TRY(begin_call(ctx));
   uint8_t* s = ctx->small.as<uint8_t>();
-  if (n) {
-    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
-    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const int K = upload_chunks(ctx, n);
+  if (n) MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+  if (K == 1) {
+    if (n) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MZ_TRY(myzkp_kzg_open_dev(ctx, ctx->scalars.p, n, u_le, s + kSmallY, s + kSmallPoint));
+  } else {
+    // the quotient scan runs from the top coefficient down, so chunks are uploaded and
+    // consumed top first; the carry leaving a chunk (its c_0) stays on the device
+    MZ_TRY(enqueue_chunk_uploads(ctx, coefs_le, ctx->scalars.as<uint8_t>(), n, K, true));
+    MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
+    XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
+    uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallY);          // carry chain, ends as y
+    uint32_t* c0_prev = reinterpret_cast<uint32_t*>(s + kSmallY + 32);
+    int* flag = reinterpret_cast<int*>(s + kSmallFlag);
+    const size_t per = (n + K - 1) / K;
+    for (int k = K - 1; k >= 0; k--) {
+      size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+      if (lo >= hi) continue;
+      MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+      const uint32_t* coefs = ctx->scalars.as<uint32_t>() + lo * 8;
+      uint32_t* q = ctx->scalars2.as<uint32_t>() + lo * 8;
+      MZ_TRY(fr_check_canonical(ctx, coefs, hi - lo, flag));
+      const bool top = (hi == n);
+      if (!top) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(c0_prev, c0, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+      MZ_TRY(fr_range_quotient(ctx, coefs, hi - lo, u_le, nullptr, q, c0, top ? nullptr : c0_prev));
+      // q[i] = q_{lo+i} pairs with SRS point lo+i; the global top coefficient q_{n-1} is the zero carry
+      MZ_TRY(msm_xyzz(ctx, q, top ? hi - lo - 1 : hi - lo, lo, res + k));
+    }
+    MZ_TRY(sum_partials(ctx, res, (size_t)K, s + kSmallPoint));
   }
-  MZ_TRY(myzkp_kzg_open_dev(ctx, ctx->scalars.p, n, u_le, s + kSmallY, s + kSmallPoint));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_w, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
   return end_call_check_flag(ctx);

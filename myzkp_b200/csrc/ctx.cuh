@@ -10,11 +10,13 @@
 
 namespace mz {
 
-// Rows of the resident SRS table: row j holds 2^(s j) * P_i for every SRS point
-// (s = table stride bits), so that an MSM with window c (a multiple of s) needs no
-// doublings at all: sum_w 2^(c w) d_w P = sum_w d_w * row[(c/s) w].
-// s = 4 -> 64 rows (c in {4,8,...,24}); s = 8 -> 32 rows (c in {8,16,24}) for very large SRS.
-constexpr int kMaxTableRows = 64;  // s * rows = 256 >= 255 bits (254-bit scalar + sign carry)
+// Rows of the resident SRS table: row j holds 2^(b_j) * P_i for every SRS point, for a
+// set of bit offsets b_j, so that an MSM with window c needs no doublings at all:
+// sum_w 2^(c w) d_w P = sum_w d_w * row[bit = c w].  The offsets are the union of
+// {c w} over the supported windows: multiples of 4 (c in {4,8,...,24}) plus the
+// multiples of 22 (c = 22, the best window around 2^22..2^24 points); a very large SRS
+// falls back to multiples of 8 (c in {8,16,24}).
+constexpr int kMaxTableRows = 80;
 
 struct DevBuf {
   void* p = nullptr;
@@ -60,8 +62,12 @@ struct myzkp_ctx {
   // resident SRS table: table_rows rows of srs_n affine points (Montgomery)
   mz::Affine* table = nullptr;
   size_t srs_n = 0;
-  int table_stride = 4;  // bits between consecutive rows
-  int table_rows = 64;
+  int table_rows = 0;
+  int row_bits[mz::kMaxTableRows] = {};   // sorted bit offsets of the rows
+  uint8_t row_of_bit[256] = {};           // bit offset -> row (0xff = absent)
+  uint32_t windows = 0;                   // bit c set <=> window c is supported
+  uint8_t* d_row_of_bit = nullptr;        // device copies
+  int* d_row_bits = nullptr;
 
   // fixed-base comb table of G for srs_generate: [32][256] affine
   mz::Affine* gcomb = nullptr;
@@ -76,6 +82,13 @@ struct myzkp_ctx {
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
   mz::DevBuf xyzz_tmp;     // XYZZ temporaries (SRS generation)
+  // host-API upload pipeline: chunks of a large polynomial are copied on copy_stream
+  // while earlier chunks are already being committed on `stream`
+  int upload_chunks = 0;  // 0 = automatic
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {};
+  cudaEvent_t copy_done_ev = nullptr;
+
   // optional per-phase CUDA-event timing of the last MSM (bench.py roofline)
   // phases: 0 recode, 1 sort, 2 accumulate, 3 merge heads, 4 bucket reduce + tree sum
   // a ring of kPhaseSlots MSM calls so a timed loop can be read back after its final sync
@@ -135,7 +148,7 @@ int fr_range_eval(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8
 // with c_i = f_{lo+i} + u c_{i+1} and c_n = carry: d_q[i] = c_{i+1} (= q_{lo+i}), *d_c0 = c_0
 // (carry_le == NULL means 0)
 int fr_range_quotient(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
-                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0);
+                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0, const uint32_t* d_carry = nullptr);
 int fr_fold(myzkp_ctx* ctx, const uint32_t* d_in, size_t n_out, const uint32_t* d_rho, uint32_t* d_out);
 int fr_check_canonical(myzkp_ctx* ctx, const uint32_t* d_in, size_t n, int* d_flag);
 

@@ -59,10 +59,10 @@ __device__ __forceinline__ XYZZ load_xyzz(const XYZZ* p) {
 // digits d_w in (-2^(c-1), 2^(c-1)], sum_w d_w 2^(c w) = scalar.  W*c >= 255
 // guarantees the top window absorbs the last carry for any scalar < 2^254.
 // key = |d| - 1 in [0, 2^(c-1)), or `sentinel` = 2^(c-1) for d == 0 (sorted to
-// the end and ignored).  val = sign << 31 | (row(w) * srs_n + srs_off + i).
+// the end and ignored).  val = sign << 31 | (row_of_bit[c w] * srs_n + srs_off + i).
 __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ scalars, size_t n, int c, int W,
-                                                  int stride_bits, uint32_t srs_n, uint32_t srs_off,
-                                                  uint32_t* __restrict__ keys,
+                                                  const uint8_t* __restrict__ row_of_bit, uint32_t srs_n,
+                                                  uint32_t srs_off, uint32_t* __restrict__ keys,
                                                   uint32_t* __restrict__ vals, int* __restrict__ flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -76,7 +76,6 @@ __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ s
   if (!fe_is_canonical(sc)) atomicOr(flag, 1);
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
-  const uint32_t rows_per_window = (uint32_t)(c / stride_bits);
   uint32_t carry = 0;
   for (int w = 0; w < W; w++) {
     int bit = w * c;
@@ -92,7 +91,7 @@ __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ s
     uint32_t mag = neg ? ((1u << c) - d) : d;
     carry = neg;
     uint32_t key = mag ? mag - 1 : half;
-    uint32_t idx = (uint32_t)w * rows_per_window * srs_n + srs_off + (uint32_t)i;
+    uint32_t idx = (uint32_t)row_of_bit[bit] * srs_n + srs_off + (uint32_t)i;
     keys[(size_t)w * n + i] = key;
     vals[(size_t)w * n + i] = idx | (neg << 31);
   }
@@ -248,18 +247,23 @@ __global__ void xyzz_set_inf(XYZZ* out) { store_xyzz(out, xyzz_inf()); }
 // accumulate 0.161 ns per entry, radix sort 0.0067 ns per entry per 8-bit pass, bucket
 // reduce max(0.35 ms latency floor, ~0.74..1.9 ns per bucket).
 static int pick_window(const myzkp_ctx* ctx, size_t n) {
-  const int s = ctx->table_stride;
-  if (ctx->window_bits >= s && ctx->window_bits <= 24 && ctx->window_bits % s == 0) return ctx->window_bits;
-  int best = s;
+  const int forced = ctx->window_bits;
+  if (forced >= 1 && forced <= 24 && ((ctx->windows >> forced) & 1)) return forced;
+  int best = 0;
   double best_t = 1e300;
-  for (int c = s; c <= 24; c += s) {
+  for (int c = 1; c <= 24; c++) {
+    if (!((ctx->windows >> c) & 1)) continue;
     if (c < 8 && n > 64) continue;
     const double W = (255 + c - 1) / c;
     const double entries = W * (double)n;
     const double nb = (double)(1u << (c - 1));
-    double reduce = nb * (nb >= (double)(1u << 22) ? 0.74 : 1.95);
+    double reduce = nb * (nb >= (double)(1u << 22) ? 0.74 : 1.3);
     if (reduce < 350000.0) reduce = 350000.0 * (c >= 16 ? 1.0 : 0.6);
-    double t = entries * (0.161 + 0.0067 * ((c + 7) / 8)) + reduce;
+    // short runs cannot fill the machine: below ~64 k segments the accumulate is latency-bound
+    double acc = entries * 0.161;
+    const double min_acc = 8.0 * 2640.0;  // ns: 8 dependent mixed adds
+    if (acc < min_acc) acc = min_acc;
+    double t = acc + entries * 0.0067 * ((c + 7) / 8) + reduce;
     if (t < best_t) { best_t = t; best = c; }
   }
   return best;
@@ -313,7 +317,7 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   ctx->phase_valid[slot] = false;
   MZ_PHASE(0);
   // 1. recode
-  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, ctx->table_stride,
+  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, ctx->d_row_of_bit,
                                                                    (uint32_t)ctx->srs_n, (uint32_t)srs_off, keys_a,
                                                                    vals_a, flag);
   MZ_LAUNCH_CHECK(ctx);
@@ -337,8 +341,19 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
     uint64_t target_threads = (uint64_t)ctx->sm_count * 512 * 8;
     uint64_t l = (M + target_threads - 1) / target_threads;
     uint64_t avg_run = M / nb;
-    if (l < avg_run / 2) l = avg_run / 2;
+    uint64_t l_run = avg_run / 2;                 // ~2 heads per bucket ...
+    uint64_t l_fill = M / (128 * 1024);           // ... but keep >= ~128 k segments in flight
+    if (l_run > l_fill) l_run = l_fill;
+    if (l < l_run) l = l_run;
     L = (uint32_t)(l < 8 ? 8 : (l > 256 ? 256 : l));
+    // quantise to whole waves of resident blocks (4 blocks of 128 threads per SM) so
+    // the last wave is not half empty
+    const uint64_t wave = (uint64_t)ctx->sm_count * 4 * kAccThreads;
+    uint64_t waves = (M / L + wave - 1) / wave;
+    if (waves >= 2 && waves <= 64) {
+      uint64_t l2 = (M + waves * wave - 1) / (waves * wave);
+      if (l2 >= 8 && l2 <= 256) L = (uint32_t)l2;
+    }
   }
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
@@ -358,7 +373,9 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 
   MZ_PHASE(4);
   // 5. bucket reduce + tree sum
-  uint32_t Lb = nb >= (1u << 22) ? 64 : (nb >= (1u << 20) ? 16 : 8);
+  // chunk length: about one wave of (3 blocks x 128 threads) per SM
+  uint32_t Lb = 8;
+  while (Lb < 64 && (uint64_t)nb / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
   uint32_t nchunks = (nb + Lb - 1) / Lb;
   MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));

@@ -180,12 +180,14 @@ __global__ void poly_check_canonical(const uint32_t* in, size_t n, int* flag) {
 // small-buffer layout (ctx->small, 4 KiB): see also msm.cu
 //   [0,32)    u / rho staged        [32,64)  carry staged
 //   [64,...)  upw[0..8] (9 * 32 B)  [512,..) misc outputs
-static int stage_small(myzkp_ctx* ctx, const uint8_t u_le[32], const uint8_t carry_le[32]) {
+static int stage_small(myzkp_ctx* ctx, const uint8_t u_le[32], const uint8_t carry_le[32],
+                       const uint32_t* d_carry = nullptr) {
   MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
   uint8_t* s = ctx->small.as<uint8_t>();
   // pageable 32-byte sources: cudaMemcpyAsync stages them before returning
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(s, u_le, 32, cudaMemcpyHostToDevice, ctx->stream));
-  if (carry_le) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(s + 32, carry_le, 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (d_carry) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(s + 32, d_carry, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  else if (carry_le) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(s + 32, carry_le, 32, cudaMemcpyHostToDevice, ctx->stream));
   else MZ_CUDA_TRY(ctx, cudaMemsetAsync(s + 32, 0, 32, ctx->stream));
   poly_small_powers<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(s), reinterpret_cast<Fr*>(s + 64));
   MZ_LAUNCH_CHECK(ctx);
@@ -209,9 +211,9 @@ int fr_range_eval(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8
 }
 
 int fr_range_quotient(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
-                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0) {
+                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0, const uint32_t* d_carry) {
   if (n == 0) return MYZKP_OK;
-  MZ_TRY(stage_small(ctx, u_le, carry_le));
+  MZ_TRY(stage_small(ctx, u_le, carry_le, d_carry));
   uint8_t* s = ctx->small.as<uint8_t>();
   size_t ntiles = (n + kPolyTile - 1) / kPolyTile;
   MZ_CUDA_TRY(ctx, ctx->poly_tiles.ensure(ntiles * (sizeof(FrMap) + 32)));

@@ -4,7 +4,7 @@
 // double-and-add scalar multiplication per point.  Here: alpha^i on the device
 // (Fr), a fixed-base comb of G (32 x 255 precomputed multiples, 8-bit digits,
 // <= 32 mixed adds per point), batched to-affine, and then the table rows
-// row[j][i] = 2^(8j) * P_i that let every MSM window reuse one bucket set.
+// row[j][i] = 2^(b_j) * P_i that let every MSM window reuse one bucket set.
 #include "ctx.cuh"
 
 namespace mz {
@@ -45,7 +45,8 @@ __global__ void srs_export(const Affine* row0, size_t n, uint32_t* out) {
 }
 
 // rows 1..rows-1 from row 0: Jacobian doubling chain, one batched inversion per point
-__global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int rows, int stride_bits) {
+__global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int rows,
+                                                      const int* __restrict__ row_bits) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine p = tbl[i];
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int
   Fq pref[kMaxTableRows - 1];
   for (int j = 1; j < rows; j++) {
 #pragma unroll 1
-    for (int d = 0; d < stride_bits; d++) jac_dbl(cur);
+    for (int d = row_bits[j - 1]; d < row_bits[j]; d++) jac_dbl(cur);
     Affine un;  // unnormalised X, Y parked in the table slot
     un.x = cur.x; un.y = cur.y;
     tbl[(size_t)j * n + i] = un;
@@ -164,6 +165,25 @@ __global__ void srs_set_generator(Affine* out) {
 }
 
 // ---------------------------------------------------------------------------
+// choose the supported windows / table rows for an SRS of n points
+static void plan_rows(myzkp_ctx* ctx, uint32_t windows) {
+  bool used[256] = {};
+  for (int c = 1; c <= 24; c++) {
+    if (!((windows >> c) & 1)) continue;
+    const int W = (255 + c - 1) / c;
+    for (int w = 0; w < W; w++) used[c * w] = true;  // c*w <= 252 for every c here
+  }
+  ctx->windows = windows;
+  ctx->table_rows = 0;
+  for (int b = 0; b < 256; b++) {
+    ctx->row_of_bit[b] = 0xff;
+    if (used[b]) {
+      ctx->row_of_bit[b] = (uint8_t)ctx->table_rows;
+      ctx->row_bits[ctx->table_rows++] = b;
+    }
+  }
+}
+
 int srs_alloc(myzkp_ctx* ctx, size_t n) {
   if (ctx->table) {
     cudaFree(ctx->table);
@@ -171,16 +191,21 @@ int srs_alloc(myzkp_ctx* ctx, size_t n) {
     ctx->srs_n = 0;
   }
   if (n == 0) return MYZKP_OK;
-  // stride 4 (64 rows) when the table fits comfortably, else stride 8 (32 rows)
   size_t free_b = 0, total_b = 0;
   MZ_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-  ctx->table_stride = 4;
-  ctx->table_rows = 64;
-  if ((uint64_t)n * 64 >= (1ull << 31) || (double)n * 64 * sizeof(Affine) > 0.55 * (double)free_b) {
-    ctx->table_stride = 8;
-    ctx->table_rows = 32;
-  }
+  const uint32_t full = (1u << 4) | (1u << 8) | (1u << 12) | (1u << 16) | (1u << 20) | (1u << 22) | (1u << 24);
+  const uint32_t lean = (1u << 8) | (1u << 16) | (1u << 24);
+  plan_rows(ctx, full);
+  if ((uint64_t)n * ctx->table_rows >= (1ull << 31) ||
+      (double)n * ctx->table_rows * sizeof(Affine) > 0.55 * (double)free_b)
+    plan_rows(ctx, lean);
   if ((uint64_t)n * ctx->table_rows >= (1ull << 31)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "SRS too large (n * rows must be < 2^31)");
+  if (!ctx->d_row_of_bit) {
+    MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_row_of_bit, 256));
+    MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_row_bits, sizeof(int) * kMaxTableRows));
+  }
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_row_of_bit, ctx->row_of_bit, 256, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_row_bits, ctx->row_bits, sizeof(int) * kMaxTableRows, cudaMemcpyHostToDevice, ctx->stream));
   MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->table, n * ctx->table_rows * sizeof(Affine)));
   ctx->srs_n = n;
   return MYZKP_OK;
@@ -189,7 +214,7 @@ int srs_alloc(myzkp_ctx* ctx, size_t n) {
 int srs_build_from_row0(myzkp_ctx* ctx) {
   size_t n = ctx->srs_n;
   if (n == 0) return MYZKP_OK;
-  srs_build_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->table, n, ctx->table_rows, ctx->table_stride);
+  srs_build_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->table, n, ctx->table_rows, ctx->d_row_bits);
   MZ_LAUNCH_CHECK(ctx);
   return MYZKP_OK;
 }
@@ -201,7 +226,12 @@ static int ensure_gcomb(myzkp_ctx* ctx) {
   MZ_CUDA_TRY(ctx, cudaMalloc(&base2, kCombRows * sizeof(Affine)));
   srs_set_generator<<<1, 1, 0, ctx->stream>>>(base2);
   MZ_LAUNCH_CHECK(ctx);
-  srs_build_rows<<<1, 128, 0, ctx->stream>>>(base2, 1, kCombRows, 8);
+  int comb_bits[kCombRows];
+  for (int j = 0; j < kCombRows; j++) comb_bits[j] = 8 * j;
+  int* d_comb_bits = nullptr;
+  MZ_CUDA_TRY(ctx, cudaMalloc(&d_comb_bits, sizeof(comb_bits)));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_comb_bits, comb_bits, sizeof(comb_bits), cudaMemcpyHostToDevice, ctx->stream));
+  srs_build_rows<<<1, 128, 0, ctx->stream>>>(base2, 1, kCombRows, d_comb_bits);
   MZ_LAUNCH_CHECK(ctx);
   const int total = kCombRows * 256;
   MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((size_t)total * sizeof(XYZZ)));
@@ -213,6 +243,7 @@ static int ensure_gcomb(myzkp_ctx* ctx) {
   MZ_LAUNCH_CHECK(ctx);
   MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   cudaFree(base2);
+  cudaFree(d_comb_bits);
   return MYZKP_OK;
 }
 

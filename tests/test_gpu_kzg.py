@@ -103,7 +103,7 @@ def test_window_sizes_and_segments_agree(ctx):
     ctx.srs_generate(alpha, n)
     exp = o.expected_commit(ints, alpha)
     try:
-        for c in (4, 8, 12, 16, 20, 24):
+        for c in (4, 8, 12, 16, 20, 22, 24):
             for seg in (0, 1, 7, 1000):
                 ctx.set_msm_params(c, seg)
                 assert ctx.commit(coefs) == exp, (c, seg)
@@ -129,7 +129,7 @@ def test_scalar_distributions(ctx):
     }
     for name, sc in dists.items():
         exp = o.expected_commit(sc, alpha)
-        for c in (4, 8, 12, 16, 20, 24):
+        for c in (4, 8, 12, 16, 20, 22, 24):
             ctx.set_msm_params(c, 0)
             assert ctx.commit(sc) == exp, (name, c)
     ctx.set_msm_params(0, 0)
@@ -237,3 +237,24 @@ def test_sharded_commit_and_open_emulated_ranks(ctx):
     assert mz.context.point_from_bytes(out.cpu().numpy().tobytes()) == ew
     for c, _, _ in ranks:
         c.close()
+
+
+def test_chunked_upload_pipeline(ctx):
+    """Host-buffer commit/open split into upload chunks (auto from 2^23) - forced here at a small size."""
+    n = 5003
+    alpha, u = 0x77777777777777777, 0x123456789
+    coefs = synth.random_scalars(n, 21)
+    ints = synth.limbs_to_ints(coefs)
+    ctx.srs_generate(alpha, n)
+    exp_c = o.expected_commit(ints, alpha)
+    exp_o = o.expected_open(ints, u, alpha)
+    try:
+        for k in (1, 2, 3, 4, 7):
+            ctx.set_upload_chunks(k)
+            assert ctx.commit(coefs) == exp_c, k
+            assert ctx.open(coefs, u) == exp_o, k
+        ctx.set_upload_chunks(4)
+        assert ctx.open([5, 7], 3) == o.expected_open([5, 7], 3, alpha)  # fewer coefficients than chunks
+        assert ctx.commit([9]) == o.expected_commit([9], alpha)
+    finally:
+        ctx.set_upload_chunks(0)

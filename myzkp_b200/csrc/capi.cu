@@ -106,7 +106,7 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   if (ctx->d_row_of_bit) cudaFree(ctx->d_row_of_bit);
   if (ctx->d_row_bits) cudaFree(ctx->d_row_bits);
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->red_a, &ctx->red_b,
+                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2, &ctx->red_a, &ctx->red_b,
                     &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)

@@ -78,6 +78,7 @@ struct myzkp_ctx {
   mz::DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
+  mz::DevBuf heads2;       // ping-pong levels of the head merge
   mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)

@@ -151,7 +151,58 @@ __global__ void __launch_bounds__(kAccThreads, 4)
   }
 }
 
-// 4. the first segment whose head belongs to bucket k folds all heads of k in
+// 4. head merge.  A bucket whose run spans many segments (skewed scalars; also the top
+// window, which only holds the few leading scalar bits and so concentrates n entries on
+// a handful of buckets) leaves many heads with the same key.  They are folded level by
+// level: a thread sums kMergeFan consecutive heads by key; runs that start inside its
+// chunk are added into their bucket (it is their only writer on this level), the first
+// run becomes a head of the next level.  The last level is the serial owner merge.
+constexpr int kMergeFan = 16;
+
+__global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
+                                                       const uint32_t* __restrict__ head_keys, uint64_t T,
+                                                       uint32_t sentinel, XYZZ* __restrict__ next_heads,
+                                                       uint32_t* __restrict__ next_keys, uint64_t T2) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T2) return;
+  uint64_t s = t * kMergeFan;
+  uint64_t e = s + kMergeFan < T ? s + kMergeFan : T;
+  uint32_t cur = head_keys[s];
+  if (cur >= sentinel) {
+    next_keys[t] = sentinel;
+    return;
+  }
+  next_keys[t] = cur;
+  XYZZ acc = xyzz_inf();
+  bool first_run = true;
+  for (uint64_t i = s; i < e; i++) {
+    uint32_t k = head_keys[i];
+    if (k != cur) {
+      if (first_run) store_xyzz(next_heads + t, acc);
+      else {
+        XYZZ b = load_xyzz(buckets + cur);
+        xyzz_add(b, acc);
+        store_xyzz(buckets + cur, b);
+      }
+      first_run = false;
+      acc = xyzz_inf();
+      cur = k;
+      if (k >= sentinel) break;
+    }
+    XYZZ h = load_xyzz(heads + i);
+    xyzz_add(acc, h);
+  }
+  if (cur < sentinel) {
+    if (first_run) store_xyzz(next_heads + t, acc);
+    else {
+      XYZZ b = load_xyzz(buckets + cur);
+      xyzz_add(b, acc);
+      store_xyzz(buckets + cur, b);
+    }
+  }
+}
+
+// last level: the first head of bucket k folds all heads of k in
 __global__ void __launch_bounds__(128) msm_merge_heads(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
                                                        const uint32_t* __restrict__ head_keys, uint64_t T,
                                                        uint32_t sentinel) {
@@ -257,7 +308,7 @@ static int pick_window(const myzkp_ctx* ctx, size_t n) {
     const double W = (255 + c - 1) / c;
     const double entries = W * (double)n;
     const double nb = (double)(1u << (c - 1));
-    double reduce = nb * (nb >= (double)(1u << 22) ? 0.74 : 1.3);
+    double reduce = nb * (nb >= (double)(1u << 20) ? 0.74 : 1.3);
     if (reduce < 350000.0) reduce = 350000.0 * (c >= 16 ? 1.0 : 0.6);
     // short runs cannot fill the machine: below ~64 k segments the accumulate is latency-bound
     double acc = entries * 0.161;
@@ -366,10 +417,32 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_LAUNCH_CHECK(ctx);
 
   MZ_PHASE(3);
-  // 4. merge segment heads
-  msm_merge_heads<<<(unsigned)((T + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
-                                                                        ctx->head_keys.as<uint32_t>(), T, nb);
-  MZ_LAUNCH_CHECK(ctx);
+  // 4. merge segment heads: fan-in levels, then the serial owner merge on what is left
+  {
+    const XYZZ* cur_heads = ctx->heads.as<XYZZ>();
+    const uint32_t* cur_keys = ctx->head_keys.as<uint32_t>();
+    uint64_t Tc = T;
+    const uint64_t T2max = (T + kMergeFan - 1) / kMergeFan;
+    const size_t lvl_stride = (size_t)T2max * (sizeof(XYZZ) + sizeof(uint32_t)) + 256;
+    MZ_CUDA_TRY(ctx, ctx->heads2.ensure(2 * lvl_stride));
+    int pp = 0;
+    while (Tc > 4096) {
+      const uint64_t T2 = (Tc + kMergeFan - 1) / kMergeFan;
+      uint8_t* base = ctx->heads2.as<uint8_t>() + (size_t)pp * lvl_stride;
+      XYZZ* nh = reinterpret_cast<XYZZ*>(base);
+      uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
+      msm_merge_level<<<(unsigned)((T2 + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads,
+                                                                             cur_keys, Tc, nb, nh, nk, T2);
+      MZ_LAUNCH_CHECK(ctx);
+      cur_heads = nh;
+      cur_keys = nk;
+      Tc = T2;
+      pp ^= 1;
+    }
+    msm_merge_heads<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads, cur_keys,
+                                                                           Tc, nb);
+    MZ_LAUNCH_CHECK(ctx);
+  }
 
   MZ_PHASE(4);
   // 5. bucket reduce + tree sum

@@ -258,3 +258,25 @@ def test_chunked_upload_pipeline(ctx):
         assert ctx.commit([9]) == o.expected_commit([9], alpha)
     finally:
         ctx.set_upload_chunks(0)
+
+
+def test_heavy_buckets_hierarchical_merge(ctx):
+    """Many segments per bucket (skewed scalars, tiny segments): the fan-in head merge levels."""
+    n = 1 << 15
+    alpha = 0xDEADBEEFCAFE
+    ctx.srs_generate(alpha, n)
+    rnd = random.Random(8)
+    dists = {
+        "all_one": [1] * n,
+        "bytes": [rnd.randrange(256) for _ in range(n)],
+        "two_values": [rnd.choice([3, R - 3]) for _ in range(n)],
+        "uniform": synth.limbs_to_ints(synth.random_scalars(n, 5)),
+    }
+    try:
+        for name, sc in dists.items():
+            exp = o.expected_commit(sc, alpha)
+            for c, seg in ((8, 1), (12, 3), (16, 1), (0, 0)):
+                ctx.set_msm_params(c, seg)
+                assert ctx.commit(sc) == exp, (name, c, seg)
+    finally:
+        ctx.set_msm_params(0, 0)

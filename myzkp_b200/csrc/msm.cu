@@ -151,72 +151,41 @@ __global__ void __launch_bounds__(kAccThreads, 4)
   }
 }
 
-// 4. head merge.  A bucket whose run spans many segments (skewed scalars; also the top
-// window, which only holds the few leading scalar bits and so concentrates n entries on
-// a handful of buckets) leaves many heads with the same key.  They are folded level by
-// level: a thread sums kMergeFan consecutive heads by key; runs that start inside its
-// chunk are added into their bucket (it is their only writer on this level), the first
-// run becomes a head of the next level.  The last level is the serial owner merge.
+// 4. head merge.  Heads with the same key form a chain (consecutive, since segments are
+// in key order).  Typical chains have one or two heads, but skewed scalars - and the top
+// window, which holds only the few leading scalar bits and so concentrates n entries on a
+// handful of buckets - make chains of thousands.  Chains are cut at multiples of
+// kMergeFan: the chain's first head folds the heads up to the next cut into the bucket
+// (its only writer on this level); a head sitting on a cut sums its kMergeFan-piece into a
+// slot of the next level, where the same rule applies.  Depth log_16(longest chain).
 constexpr int kMergeFan = 16;
 
 __global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
                                                        const uint32_t* __restrict__ head_keys, uint64_t T,
                                                        uint32_t sentinel, XYZZ* __restrict__ next_heads,
-                                                       uint32_t* __restrict__ next_keys, uint64_t T2) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T2) return;
-  uint64_t s = t * kMergeFan;
-  uint64_t e = s + kMergeFan < T ? s + kMergeFan : T;
-  uint32_t cur = head_keys[s];
-  if (cur >= sentinel) {
-    next_keys[t] = sentinel;
-    return;
-  }
-  next_keys[t] = cur;
-  XYZZ acc = xyzz_inf();
-  bool first_run = true;
-  for (uint64_t i = s; i < e; i++) {
-    uint32_t k = head_keys[i];
-    if (k != cur) {
-      if (first_run) store_xyzz(next_heads + t, acc);
-      else {
-        XYZZ b = load_xyzz(buckets + cur);
-        xyzz_add(b, acc);
-        store_xyzz(buckets + cur, b);
-      }
-      first_run = false;
-      acc = xyzz_inf();
-      cur = k;
-      if (k >= sentinel) break;
-    }
-    XYZZ h = load_xyzz(heads + i);
-    xyzz_add(acc, h);
-  }
-  if (cur < sentinel) {
-    if (first_run) store_xyzz(next_heads + t, acc);
-    else {
-      XYZZ b = load_xyzz(buckets + cur);
-      xyzz_add(b, acc);
-      store_xyzz(buckets + cur, b);
-    }
-  }
-}
-
-// last level: the first head of bucket k folds all heads of k in
-__global__ void __launch_bounds__(128) msm_merge_heads(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
-                                                       const uint32_t* __restrict__ head_keys, uint64_t T,
-                                                       uint32_t sentinel) {
+                                                       uint32_t* __restrict__ next_keys) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   uint32_t k = head_keys[t];
   if (k >= sentinel) return;
-  if (t > 0 && head_keys[t - 1] == k) return;
-  XYZZ acc = load_xyzz(buckets + k);
-  for (uint64_t j = t; j < T && head_keys[j] == k; j++) {
+  const bool chain_start = (t == 0) || head_keys[t - 1] != k;
+  const bool on_cut = (t % kMergeFan) == 0;
+  if (!chain_start && !on_cut) return;
+  uint64_t end = (t / kMergeFan + 1) * kMergeFan;
+  if (end > T) end = T;
+  XYZZ acc = xyzz_inf();
+  for (uint64_t j = t; j < end && head_keys[j] == k; j++) {
     XYZZ h = load_xyzz(heads + j);
     xyzz_add(acc, h);
   }
-  store_xyzz(buckets + k, acc);
+  if (chain_start) {
+    XYZZ b = load_xyzz(buckets + k);
+    xyzz_add(b, acc);
+    store_xyzz(buckets + k, b);
+  } else {
+    store_xyzz(next_heads + t / kMergeFan, acc);
+    next_keys[t / kMergeFan] = k;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -294,30 +263,18 @@ __global__ void xyzz_set_inf(XYZZ* out) { store_xyzz(out, xyzz_inf()); }
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-// Window choice by a cost model fitted to measurements on B200 (profiles/phase_sweep_r1.json):
-// accumulate 0.161 ns per entry, radix sort 0.0067 ns per entry per 8-bit pass, bucket
-// reduce max(0.35 ms latency floor, ~0.74..1.9 ns per bucket).
+// Window choice from measurements on B200 (profiles/phase_sweep_r1*.json): per entry the
+// accumulate costs 0.161 ns and the sort 0.02 ns; the bucket reduce costs ~0.74 ns per
+// bucket with a ~0.35 ms latency floor; long head chains make small windows a bad deal
+// for small inputs.
 static int pick_window(const myzkp_ctx* ctx, size_t n) {
   const int forced = ctx->window_bits;
   if (forced >= 1 && forced <= 24 && ((ctx->windows >> forced) & 1)) return forced;
-  int best = 0;
-  double best_t = 1e300;
-  for (int c = 1; c <= 24; c++) {
-    if (!((ctx->windows >> c) & 1)) continue;
-    if (c < 8 && n > 64) continue;
-    const double W = (255 + c - 1) / c;
-    const double entries = W * (double)n;
-    const double nb = (double)(1u << (c - 1));
-    double reduce = nb * (nb >= (double)(1u << 20) ? 0.74 : 1.3);
-    if (reduce < 350000.0) reduce = 350000.0 * (c >= 16 ? 1.0 : 0.6);
-    // short runs cannot fill the machine: below ~64 k segments the accumulate is latency-bound
-    double acc = entries * 0.161;
-    const double min_acc = 8.0 * 2640.0;  // ns: 8 dependent mixed adds
-    if (acc < min_acc) acc = min_acc;
-    double t = acc + entries * 0.0067 * ((c + 7) / 8) + reduce;
-    if (t < best_t) { best_t = t; best = c; }
-  }
-  return best;
+  auto has = [&](int c) { return ((ctx->windows >> c) & 1) != 0; };
+  if (n < ((size_t)1 << 11)) return 8;
+  if (n < ((size_t)1 << 19) || !has(20)) return (n >= ((size_t)1 << 23) && !has(20)) ? 24 : 16;
+  if (n < ((size_t)1 << 23) || !has(22)) return 20;
+  return 22;
 }
 
 // tree-sum `count` XYZZ values living in buffer `a` (ping-pong with `b`); the
@@ -417,33 +374,32 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_LAUNCH_CHECK(ctx);
 
   MZ_PHASE(3);
-  // 4. merge segment heads: fan-in levels, then the serial owner merge on what is left
+  // 4. merge segment heads, level by level (levels beyond the first are nearly empty
+  //    unless some bucket spans more than 16 segments)
   {
     const XYZZ* cur_heads = ctx->heads.as<XYZZ>();
     const uint32_t* cur_keys = ctx->head_keys.as<uint32_t>();
     uint64_t Tc = T;
     const uint64_t T2max = (T + kMergeFan - 1) / kMergeFan;
-    const size_t lvl_stride = (size_t)T2max * (sizeof(XYZZ) + sizeof(uint32_t)) + 256;
+    const size_t lvl_stride = (((size_t)T2max * (sizeof(XYZZ) + sizeof(uint32_t)) + 255) / 256 + 1) * 256;
     MZ_CUDA_TRY(ctx, ctx->heads2.ensure(2 * lvl_stride));
     int pp = 0;
-    while (Tc > 4096) {
+    while (true) {
       const uint64_t T2 = (Tc + kMergeFan - 1) / kMergeFan;
       uint8_t* base = ctx->heads2.as<uint8_t>() + (size_t)pp * lvl_stride;
       XYZZ* nh = reinterpret_cast<XYZZ*>(base);
       uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
-      msm_merge_level<<<(unsigned)((T2 + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads,
-                                                                             cur_keys, Tc, nb, nh, nk, T2);
+      if (Tc > kMergeFan) MZ_CUDA_TRY(ctx, cudaMemsetAsync(nk, 0xff, T2 * sizeof(uint32_t), ctx->stream));
+      msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads, cur_keys,
+                                                                             Tc, nb, nh, nk);
       MZ_LAUNCH_CHECK(ctx);
+      if (Tc <= kMergeFan) break;  // every head was inside the first cut: nothing was forwarded
       cur_heads = nh;
       cur_keys = nk;
       Tc = T2;
       pp ^= 1;
     }
-    msm_merge_heads<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads, cur_keys,
-                                                                           Tc, nb);
-    MZ_LAUNCH_CHECK(ctx);
   }
-
   MZ_PHASE(4);
   // 5. bucket reduce + tree sum
   // chunk length: about one wave of (3 blocks x 128 threads) per SM

@@ -99,6 +99,16 @@ int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const si
 int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_pow2,
                              const uint8_t* rhos_le /* m*32 */, uint8_t* out /* (m+1)*64 */,
                              uint8_t* out_folds /* (n_pow2-1)*32 or NULL */);
+/* batch_open_kzg (kzg.rs:74-88): ys[i] = f(us[i]); W = commit((f - I)/Z) with I the
+ * interpolant of (us, ys) and Z = prod (x - us[i]).  Since deg I < k the quotient is the
+ * floor quotient of f by Z, computed as k successive (x - u_i) divisions.  k <= 64;
+ * the us must be distinct (the reference's interpolate divides by their differences). */
+int myzkp_kzg_batch_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t* us_le /* k*32 */, size_t k,
+                         uint8_t* out_ys /* k*32 */, uint8_t out_w[64]);
+/* prove_degree_bound (kzg.rs:121-134): commitment to f * x^(max_d - d), i.e. an MSM of
+ * f against the SRS window starting at max_d - d (max_d = srs_len - 1).  deg f > d is
+ * an error (the reference index-panics). */
+int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, size_t d, uint8_t out_p[64]);
 /* Polynomial::eval (polynomial.rs:120-128). */
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]);
 /* y and the quotient coefficients themselves (n-1 of them; n >= 1). */
@@ -131,7 +141,8 @@ int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, c
                                 const uint8_t carry_in_le[32], void* d_q /* n*32 */, void* d_c0 /* 32 */);
 
 /* ---- test hooks: batched field / group ops for parity tests -------------
- * op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 neg(a);  field: 0 = Fq, 1 = Fr.
+ * op: 0 add, 1 sub, 2 mul, 3 inverse(a) (Fermat), 4 neg(a), 5 inverse(a) (binary GCD);
+ * field: 0 = Fq, 1 = Fr.
  * Inputs/outputs canonical 32 B LE, host pointers. */
 int myzkp_test_field_op(myzkp_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
                         uint8_t* out, size_t n);

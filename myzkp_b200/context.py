@@ -156,6 +156,22 @@ class Context:
         self._ck(self._lib.myzkp_kzg_open(self.h, _ptr(a), a.shape[0], _ptr(ub), _ptr(y), _ptr(w)))
         return bytes_to_int(y), point_from_bytes(w)
 
+    def batch_open(self, coefs, us):
+        a = scalars_to_bytes(coefs)
+        ub = scalars_to_bytes([int(u) for u in us])
+        k = ub.shape[0]
+        ys = np.zeros((k, 32), np.uint8)
+        w = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_kzg_batch_open(self.h, _ptr(a), a.shape[0], _ptr(ub) if k else None, k,
+                                                _ptr(ys) if k else None, _ptr(w)))
+        return [bytes_to_int(ys[i]) for i in range(k)], point_from_bytes(w)
+
+    def prove_degree_bound(self, coefs, d: int):
+        a = scalars_to_bytes(coefs)
+        out = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_kzg_prove_degree_bound(self.h, _ptr(a), a.shape[0], d, _ptr(out)))
+        return point_from_bytes(out)
+
     def fr_eval(self, coefs, u: int) -> int:
         a = scalars_to_bytes(coefs)
         ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()

@@ -369,6 +369,66 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
   return end_call_check_flag(ctx);
 }
 
+int myzkp_kzg_batch_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t* us_le, size_t k,
+                         uint8_t* out_ys, uint8_t out_w[64]) {
+  if (!ctx || (!coefs_le && n) || (k && (!us_le || !out_ys)) || !out_w || k > 64) return MYZKP_ERR_INVALID_ARG;
+  for (size_t i = 0; i < k; i++)
+    if (!fr_bytes_canonical(us_le + 32 * i)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  const size_t nq = n > k ? n - k : 0;  // quotient length
+  if (nq > ctx->srs_n || (nq && !ctx->table))
+    return fail(ctx, !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG, "quotient longer than the SRS");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  int* flag = reinterpret_cast<int*>(s + kSmallFlag);
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure((n ? n : 1) * 32));
+  MZ_CUDA_TRY(ctx, ctx->scalars2.ensure((n ? n : 1) * 32));
+  MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure(k * 32 + 64));
+  uint32_t* d_ys = ctx->xyzz_tmp.as<uint32_t>();
+  uint32_t* d_scratch = d_ys + 8 * k;  // (u^n, c0) sinks
+  if (n) {
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MZ_TRY(fr_check_canonical(ctx, ctx->scalars.as<uint32_t>(), n, flag));
+  }
+  // ys[i] = f(u_i) (kzg.rs:79)
+  for (size_t i = 0; i < k; i++)
+    MZ_TRY(fr_range_eval(ctx, ctx->scalars.as<uint32_t>(), n, us_le + 32 * i, d_ys + 8 * i, d_scratch));
+  // (f - I)/Z with deg I < k: floor division by prod (x - u_i) = k successive synthetic divisions
+  uint32_t* cur = ctx->scalars.as<uint32_t>();
+  uint32_t* nxt = ctx->scalars2.as<uint32_t>();
+  size_t len = n;
+  for (size_t i = 0; i < k && len > 0; i++) {
+    MZ_TRY(fr_range_quotient(ctx, cur, len, us_le + 32 * i, nullptr, nxt, d_scratch + 8));
+    uint32_t* t = cur; cur = nxt; nxt = t;
+    len -= 1;  // q has len-1 coefficients (the top one written is the zero carry)
+  }
+  XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
+  MZ_TRY(msm_xyzz(ctx, cur, n > k ? len : 0, 0, res));
+  MZ_TRY(xyzz_to_bytes(ctx, res, 1, s + kSmallPoint));
+  if (k) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_ys, d_ys, k * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_w, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
+int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, size_t d, uint8_t out_p[64]) {
+  if (!ctx || (!coefs_le && n) || !out_p) return MYZKP_ERR_INVALID_ARG;
+  if (!ctx->table || ctx->srs_n == 0) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
+  const size_t max_d = ctx->srs_n - 1;
+  if (d > max_d) return fail(ctx, MYZKP_ERR_INVALID_ARG, "degree bound above max_d (reference underflows at kzg.rs:127)");
+  const size_t shift = max_d - d;  // commit to f * x^(max_d - d)  (kzg.rs:126-133)
+  if (n + shift > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "deg f > d: shifted polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  if (n) {
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
+  MZ_TRY(msm_xyzz(ctx, ctx->scalars.as<uint32_t>(), n, shift, res));
+  MZ_TRY(xyzz_to_bytes(ctx, res, 1, s + kSmallPoint));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_p, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return end_call_check_flag(ctx);
+}
+
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]) {
   if (!ctx || (!coefs_le && n) || !u_le || !out_y) return MYZKP_ERR_INVALID_ARG;
   if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");

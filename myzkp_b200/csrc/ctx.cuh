@@ -138,6 +138,11 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
 int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);
 
+// ---- sort.cu ----
+// LSD radix sort of (key, val) pairs by the low `bits` key bits; result in (*out_keys, *out_vals)
+int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
+                     int bits, uint32_t** out_keys, uint32_t** out_vals);
+
 // ---- srs.cu ----
 int srs_alloc(myzkp_ctx* ctx, size_t n);
 int srs_build_from_row0(myzkp_ctx* ctx);  // fills rows 1.. from row 0 (Montgomery affine)

@@ -353,6 +353,84 @@ MZ_HD Fe<PR> fe_inv(const Fe<PR>& a) {
   return r;
 }
 
+// Latency-oriented inverse for the one-off final to-affine of a commitment: binary
+// extended GCD on the raw residue (variable time - the data is public), ~5x fewer
+// dependent cycles for a lone thread than the 380-multiply Fermat ladder above.
+// Input/output in Montgomery form; inverse(0) = 0.
+namespace detail {
+template <class PR>
+MZ_HD bool limbs_is_one(const uint32_t* a) {
+  uint32_t o = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) o |= a[i];
+  return o == 0;
+}
+MZ_HD void limbs_shr1(uint32_t* a, uint32_t top) {  // a = (top:a) >> 1
+#pragma unroll
+  for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+  a[7] = (a[7] >> 1) | (top << 31);
+}
+// x = x/2 mod m for x in [0, m)
+template <class PR>
+MZ_HD void limbs_half_mod(uint32_t* x) {
+  uint32_t carry = 0;
+  if (x[0] & 1u) {
+    x[0] = add_cc(x[0], mod_limb<PR>(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) x[i] = addc_cc(x[i], mod_limb<PR>(i));
+    carry = addc(0, 0);
+  }
+  limbs_shr1(x, carry);
+}
+MZ_HD bool limbs_geq(const uint32_t* a, const uint32_t* b) {  // a >= b
+  (void)sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) (void)subc_cc(a[i], b[i]);
+  return subc(0, 0) == 0;
+}
+MZ_HD void limbs_sub(uint32_t* a, const uint32_t* b) {  // a -= b (a >= b)
+  a[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) a[i] = subc_cc(a[i], b[i]);
+  a[7] = subc(a[7], b[7]);
+}
+}  // namespace detail
+
+template <class PR>
+MZ_HD Fe<PR> fe_inv_bingcd(const Fe<PR>& a) {
+  if (a.is_zero()) return a;
+  uint32_t u[8], v[8];
+  Fe<PR> x1, x2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = a.v[i];
+    v[i] = mod_limb<PR>(i);
+    x1.v[i] = 0;
+    x2.v[i] = 0;
+  }
+  x1.v[0] = 1;
+  // invariants: x1 * a == u, x2 * a == v (mod m)
+  while (!detail::limbs_is_one<PR>(u) && !detail::limbs_is_one<PR>(v)) {
+    while ((u[0] & 1u) == 0) {
+      detail::limbs_shr1(u, 0);
+      detail::limbs_half_mod<PR>(x1.v);
+    }
+    while ((v[0] & 1u) == 0) {
+      detail::limbs_shr1(v, 0);
+      detail::limbs_half_mod<PR>(x2.v);
+    }
+    if (detail::limbs_geq(u, v)) {
+      detail::limbs_sub(u, v);
+      x1 = fe_sub(x1, x2);
+    } else {
+      detail::limbs_sub(v, u);
+      x2 = fe_sub(x2, x1);
+    }
+  }
+  Fe<PR> r = detail::limbs_is_one<PR>(u) ? x1 : x2;  // r = (aR)^-1 = a^-1 R^-1
+  return fe_mul(fe_mul(r, Fe<PR>::r2()), Fe<PR>::r2());  // -> a^-1 R
+}
+
 typedef Fe<FqParams> Fq;
 typedef Fe<FrParams> Fr;
 

@@ -140,7 +140,7 @@ MZ_HD Affine xyzz_to_affine_with_inv(const XYZZ& p, const Fq& izzz) {
 }
 MZ_HD Affine xyzz_to_affine(const XYZZ& p) {
   if (xyzz_is_inf(p)) { Affine z; z.x = Fq::zero(); z.y = Fq::zero(); return z; }
-  return xyzz_to_affine_with_inv(p, fe_inv(p.zzz));
+  return xyzz_to_affine_with_inv(p, fe_inv_bingcd(p.zzz));
 }
 
 // Jacobian doubling, a = 0 (2M + 5S): A=X^2 B=Y^2 C=B^2 D=2((X+B)^2-A-C)

@@ -8,7 +8,8 @@
 //                      index | sign) entry per non-zero digit.  Because table
 //                      row j holds 2^(8j) P_i, every window shares ONE set of
 //                      2^(c-1) buckets and no doublings are ever needed.
-//   2. radix sort      entries by bucket key (cub::DeviceRadixSort, c bits).
+//   2. radix sort      entries by bucket key (sort.cu: hand-written LSD radix sort,
+//                      8 bits per pass, c bits).
 //   3. msm_accumulate  fixed-length segments of the sorted entry list, one
 //                      thread each, XYZZ mixed adds; load-balanced for any
 //                      scalar distribution (a heavy bucket just spans segments).
@@ -16,8 +17,6 @@
 //                      partial to the bucket's owner.
 //   5. msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
 //                      running sums, then a tree sum.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "ctx.cuh"
 
 namespace mz {
@@ -332,13 +331,8 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 
   MZ_PHASE(1);
   // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit)
-  size_t tmp_bytes = 0;
-  MZ_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, M, 0, c,
-                                                   ctx->stream));
-  MZ_CUDA_TRY(ctx, ctx->sort_tmp.ensure(tmp_bytes));
-  MZ_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, keys_a, keys_b, vals_a, vals_b, M, 0,
-                                                   c, ctx->stream));
-  ctx->launches += (c + 7) / 8 + 2;  // onesweep: histogram + scan + one kernel per 8-bit pass
+  uint32_t *keys_s = nullptr, *vals_s = nullptr;
+  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, c, &keys_s, &vals_s));
 
   // 3. accumulate
   // Segment length: enough segments to fill the GPU several times over, but not much
@@ -369,7 +363,7 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(2);
   msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-      keys_b, vals_b, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+      keys_s, vals_s, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
       ctx->head_keys.as<uint32_t>(), T);
   MZ_LAUNCH_CHECK(ctx);
 

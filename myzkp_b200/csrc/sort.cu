@@ -1,0 +1,244 @@
+// Hand-written LSD radix sort of the MSM's (bucket key, point index) pairs.
+//
+// 8 bits per pass, ceil(c/8) passes for a c-bit key.  Each pass is three kernels:
+//   sort_tile_hist    per-tile digit histogram (tile = 256 threads x 16 entries),
+//                     written digit-major so one exclusive scan gives every
+//                     (digit, tile) its global base
+//   scan_*            exclusive scan of the 256 x tiles counters
+//   sort_tile_scatter stable multi-split of the tile in shared memory (per-warp
+//                     digit counters + __match_any_sync ranking), then a coalesced
+//                     copy-out of each digit run to its global base
+// Per pass and entry: 4 B (histogram read) + 8 B read + 8 B write = 20 B of HBM traffic.
+// Stability is not needed by the MSM (bucket sums commute) but keeps the sort a plain
+// LSD radix sort whose result is independent of scheduling.
+#include "ctx.cuh"
+
+namespace mz {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 entries
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRadix = 256;
+
+// ---------------------------------------------------------------------------
+// exclusive scan of a uint32 array (reduce - scan - apply)
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += o;
+  }
+  return v;
+}
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix and the block total
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+    uint32_t si = warp_incl_scan(s);
+    warp_sums[lane] = si - s;  // exclusive warp bases
+    if (lane == 31) warp_sums[32] = si;
+  }
+  __syncthreads();
+  total = warp_sums[32];
+  uint32_t r = warp_sums[w] + incl - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_chunk_sums(const uint32_t* __restrict__ in, size_t n,
+                                                                uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[33];
+  size_t base = (size_t)blockIdx.x * kScanChunk;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    size_t idx = base + (size_t)i * kScanThreads + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  uint32_t total;
+  block_excl_scan(s, ws, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+// single block: in-place exclusive scan of the chunk sums
+__global__ void __launch_bounds__(kScanThreads) scan_sums_inplace(uint32_t* sums, size_t m) {
+  __shared__ uint32_t ws[33];
+  uint32_t carry = 0;
+  for (size_t base = 0; base < m; base += kScanThreads) {
+    size_t idx = base + threadIdx.x;
+    uint32_t v = idx < m ? sums[idx] : 0;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(v, ws, total);
+    if (idx < m) sums[idx] = carry + ex;
+    carry += total;
+  }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply(uint32_t* __restrict__ data, size_t n,
+                                                           const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[33];
+  size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;  // blocked: 8 consecutive per thread
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    v[i] = (base + i < n) ? data[base + i] : 0;
+    s += v[i];
+  }
+  uint32_t total;
+  uint32_t ex = block_excl_scan(s, ws, total) + sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (base + i < n) data[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pass kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+                                                               uint32_t* __restrict__ hist, uint32_t ntiles) {
+  __shared__ uint32_t h[kRadix];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSortThreads, 3)
+    sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
+                      const uint32_t* __restrict__ hist_scanned, uint32_t ntiles, uint32_t* __restrict__ keys_out,
+                      uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t s_keys[kSortTile];
+  __shared__ uint32_t s_vals[kSortTile];
+  __shared__ uint32_t cnt[kSortWarps][kRadix];  // per-warp digit counters, then per-warp bases
+  __shared__ uint32_t digit_start[kRadix];      // start of each digit run inside the tile
+  __shared__ uint32_t gbase[kRadix];            // global base of each digit run of this tile
+  __shared__ uint32_t ws[33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kSortTile;
+  const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)kSortTile ? (n - tile_base) : kSortTile);
+#pragma unroll
+  for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
+  gbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * ntiles + blockIdx.x];
+  __syncthreads();
+
+  // warp-blocked arrangement: warp w owns tile entries [w*512, (w+1)*512) in index order
+  uint32_t k[kSortItems], v[kSortItems], rank[kSortItems];
+  const uint32_t wbase = (uint32_t)w * (32 * kSortItems);
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = wbase + i * 32 + lane;
+    bool ok = p < tile_n;
+    k[i] = ok ? keys_in[tile_base + p] : 0xffffffffu;
+    v[i] = ok ? vals_in[tile_base + p] : 0u;
+    uint32_t d = ok ? ((k[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // 256 = padding, never matches a digit
+    // peers: lanes of this warp holding the same digit in this round
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t prev = 0;
+    if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter
+      prev = cnt[w][d];
+      cnt[w][d] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+    rank[i] = prev + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  // digit totals -> exclusive scan over digits -> per-warp bases
+  {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int i = 0; i < kSortWarps; i++) tot += cnt[i][threadIdx.x];
+    uint32_t total;
+    uint32_t ex = block_excl_scan(tot, ws, total);
+    digit_start[threadIdx.x] = ex;
+    uint32_t run = ex;
+#pragma unroll
+    for (int i = 0; i < kSortWarps; i++) {
+      uint32_t c = cnt[i][threadIdx.x];
+      cnt[i][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // place into shared memory in digit order
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = wbase + i * 32 + lane;
+    if (p < tile_n) {
+      uint32_t d = (k[i] >> shift) & (kRadix - 1);
+      uint32_t pos = cnt[w][d] + rank[i];
+      s_keys[pos] = k[i];
+      s_vals[pos] = v[i];
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out of the digit runs
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
+    if (p < tile_n) {
+      uint32_t key = s_keys[p];
+      uint32_t d = (key >> shift) & (kRadix - 1);
+      uint64_t g = (uint64_t)gbase[d] + (p - digit_start[d]);
+      keys_out[g] = key;
+      vals_out[g] = s_vals[p];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+// Sorts n (key, val) pairs by the low `bits` key bits.  The result lands in
+// (*out_keys, *out_vals), which alias either the a- or the b-buffers.
+int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
+                     int bits, uint32_t** out_keys, uint32_t** out_vals) {
+  *out_keys = keys_a;
+  *out_vals = vals_a;
+  if (n == 0 || bits <= 0) return MYZKP_OK;
+  if (n >= (1ull << 32)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "too many entries to sort");
+  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  const size_t hist_len = (size_t)ntiles * kRadix;
+  const size_t nchunks = (hist_len + kScanChunk - 1) / kScanChunk;
+  MZ_CUDA_TRY(ctx, ctx->sort_tmp.ensure((hist_len + nchunks + 64) * sizeof(uint32_t)));
+  uint32_t* hist = ctx->sort_tmp.as<uint32_t>();
+  uint32_t* sums = hist + hist_len;
+  uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+  for (int shift = 0; shift < bits; shift += 8) {
+    sort_tile_hist<<<ntiles, kSortThreads, 0, ctx->stream>>>(ki, n, shift, hist, ntiles);
+    MZ_LAUNCH_CHECK(ctx);
+    scan_chunk_sums<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
+    MZ_LAUNCH_CHECK(ctx);
+    scan_sums_inplace<<<1, kScanThreads, 0, ctx->stream>>>(sums, nchunks);
+    MZ_LAUNCH_CHECK(ctx);
+    scan_apply<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
+    MZ_LAUNCH_CHECK(ctx);
+    sort_tile_scatter<<<ntiles, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo);
+    MZ_LAUNCH_CHECK(ctx);
+    uint32_t* t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  *out_keys = ki;
+  *out_vals = vi;
+  return MYZKP_OK;
+}
+
+}  // namespace mz

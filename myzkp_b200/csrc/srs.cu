@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) srs_build_rows(Affine* tbl, size_t n, int
     zs[j - 1] = cur.z;
     pref[j - 1] = (j == 1) ? cur.z : fe_mul(pref[j - 2], cur.z);
   }
-  Fq inv = fe_inv(pref[rows - 2]);
+  Fq inv = fe_inv_bingcd(pref[rows - 2]);
   for (int k = rows - 2; k >= 0; k--) {
     Fq zinv = (k > 0) ? fe_mul(inv, pref[k - 1]) : inv;
     inv = fe_mul(inv, zs[k]);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) batch_to_affine(const XYZZ* in, size_t n,
     acc = fe_mul(acc, z);
     pref[k] = acc;
   }
-  Fq inv = fe_inv(acc);
+  Fq inv = fe_inv_bingcd(acc);
   for (int k = cnt - 1; k >= 0; k--) {
     XYZZ p = in[lo + k];
     Affine o;

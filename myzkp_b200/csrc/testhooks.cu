@@ -32,6 +32,7 @@ __global__ void test_field_kernel(int op, const uint32_t* a, const uint32_t* b, 
     case 1: r = fe_sub(x, y); break;
     case 2: r = fe_mul(x, y); break;
     case 3: r = fe_inv(x); break;
+    case 5: r = fe_inv_bingcd(x); break;
     default: r = fe_neg(x); break;
   }
   store_fe(out + i * 8, fe_from_mont(r));
@@ -92,7 +93,7 @@ __global__ void test_g1_kernel(int op, const uint32_t* a, const uint32_t* b, uin
 
 extern "C" int myzkp_test_field_op(myzkp_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
                                    size_t n) {
-  if (!ctx || !a || !out || op < 0 || op > 4 || ((op <= 2) && !b)) return MYZKP_ERR_INVALID_ARG;
+  if (!ctx || !a || !out || op < 0 || op > 5 || ((op <= 2) && !b)) return MYZKP_ERR_INVALID_ARG;
   if (n == 0) return MYZKP_OK;
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32 * 3));

@@ -6,7 +6,7 @@ from typing import List, Sequence
 import numpy as np
 
 from .context import R_MOD, bytes_to_int
-from .kzg import G1Point, Polynomial, PublicKeyKZG
+from .kzg import BatchProofKZG, G1Point, Polynomial, PublicKeyKZG, batch_open_kzg, prove_degree_bound
 
 
 class SplitFoldError(ValueError):
@@ -42,3 +42,22 @@ def split_and_fold_commit(coef, rhos: Sequence[int], pk: PublicKeyKZG, want_fold
 def commit_gemini(polys: Sequence[Polynomial], pk: PublicKeyKZG) -> List[G1Point]:
     """gemini.rs:112-114: one commit_kzg per polynomial."""
     return [G1Point._from_tuple(pk.ctx.commit(p._wire())) for p in polys]
+
+
+class ProofGemini:
+    """gemini.rs:107-110."""
+
+    def __init__(self, es: List[BatchProofKZG], degree_proofs: List[G1Point]):
+        self.es = es
+        self.degree_proofs = degree_proofs
+
+
+def open_gemini(polys: Sequence[Polynomial], beta: int, pk: PublicKeyKZG) -> ProofGemini:
+    """gemini.rs:116-144: every polynomial but the last is opened at (beta, -beta, beta^2);
+    polynomial i gets a degree-bound proof for 2^(num_polys - i - 1)."""
+    num_polys = len(polys)
+    beta = int(beta) % R_MOD
+    us = [beta, (-beta) % R_MOD, beta * beta % R_MOD]
+    es = [batch_open_kzg(p, us, pk) for p in polys[: num_polys - 1]]
+    degree_proofs = [prove_degree_bound(p, pk, 2 ** (num_polys - i - 1)) for i, p in enumerate(polys)]
+    return ProofGemini(es, degree_proofs)

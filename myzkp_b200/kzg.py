@@ -128,3 +128,25 @@ def open_kzg(f: Polynomial, u: int, pk: PublicKeyKZG) -> ProofKZG:
     """kzg.rs:61-72."""
     y, w = pk.ctx.open(f._wire(), int(u) % R_MOD)
     return ProofKZG(y, G1Point._from_tuple(w))
+
+
+class BatchProofKZG:
+    """kzg.rs:20-23."""
+
+    def __init__(self, ys: List[int], w: G1Point):
+        self.ys = ys
+        self.w = w
+
+
+ProofDegreeBound = G1Point
+
+
+def batch_open_kzg(f: Polynomial, us: Sequence[int], pk: PublicKeyKZG) -> BatchProofKZG:
+    """kzg.rs:74-88."""
+    ys, w = pk.ctx.batch_open(f._wire(), [int(u) % R_MOD for u in us])
+    return BatchProofKZG(ys, G1Point._from_tuple(w))
+
+
+def prove_degree_bound(f: Polynomial, pk: PublicKeyKZG, d: int) -> ProofDegreeBound:
+    """kzg.rs:121-134."""
+    return G1Point._from_tuple(pk.ctx.prove_degree_bound(f._wire(), d))

@@ -409,6 +409,24 @@ class Polynomial:
     def __truediv__(self, other):  # polynomial.rs:583-597
         return self.div_rem_ref(other)[0]
 
+    @staticmethod
+    def interpolate(x_values: Sequence[FE], y_values: Sequence[FE]) -> "Polynomial":
+        """polynomial.rs:177-200: Lagrange interpolation."""
+        F = type(x_values[0])
+        lagrange_polys = []
+        numerators = Polynomial.from_monomials(x_values)
+        for j in range(len(x_values)):
+            denominator = F.one()
+            for i in range(len(x_values)):
+                if i != j:
+                    denominator = denominator * x_values[j].sub_ref(x_values[i])
+            cur_poly = numerators / Polynomial.from_monomials([x_values[j]]).scalar_mul(denominator)
+            lagrange_polys.append(cur_poly)
+        result = Polynomial([], F)
+        for j, lp in enumerate(lagrange_polys):
+            result = result + lp.scalar_mul(y_values[j])
+        return result
+
     def canonical(self) -> List[int]:
         return [c.sanitize().value for c in self.coef]
 
@@ -454,6 +472,32 @@ def open_kzg(f: Polynomial, u: Fr, pk: PublicKeyKZG) -> ProofKZG:
     return ProofKZG(y, f_u.eval_with_powers_on_curve(pk.powers_1))
 
 
+class BatchProofKZG:
+    """kzg.rs:20-23."""
+
+    def __init__(self, ys: List[Fr], w: G1Point):
+        self.ys = ys
+        self.w = w
+
+
+def batch_open_kzg(f: Polynomial, us: Sequence[Fr], pk: PublicKeyKZG) -> BatchProofKZG:
+    """kzg.rs:74-88."""
+    ys = [f.eval(z) for z in us]
+    ip = Polynomial.interpolate(us, ys)
+    z = Polynomial.from_monomials(us)
+    f_u = (f - ip) / z
+    return BatchProofKZG(ys, f_u.eval_with_powers_on_curve(pk.powers_1))
+
+
+def prove_degree_bound(f: Polynomial, pk: PublicKeyKZG, d: int) -> G1Point:
+    """kzg.rs:121-134: commit to f * x^(max_d - d)."""
+    max_d = len(pk.powers_1) - 1
+    q_coef = [Fr.zero() for _ in range(max_d + 1 - d)]
+    q_coef[max_d - d] = Fr.one()
+    r = f.mul_ref(Polynomial(q_coef, Fr))
+    return r.eval_with_powers_on_curve(pk.powers_1)
+
+
 # --- gemini.rs --------------------------------------------------------------
 class SplitFoldError(ValueError):
     """gemini.rs:15-32."""
@@ -485,6 +529,22 @@ def split_and_fold(coef: Sequence[FE], rhos: Sequence[FE]) -> List[Polynomial]:
 def commit_gemini(polys: Sequence[Polynomial], pk: PublicKeyKZG) -> List[G1Point]:
     """gemini.rs:112-114."""
     return [commit_kzg(p, pk) for p in polys]
+
+
+class ProofGemini:
+    """gemini.rs:107-110."""
+
+    def __init__(self, es: List[BatchProofKZG], degree_proofs: List[G1Point]):
+        self.es = es
+        self.degree_proofs = degree_proofs
+
+
+def open_gemini(polys: Sequence[Polynomial], beta: Fr, pk: PublicKeyKZG) -> ProofGemini:
+    """gemini.rs:116-144."""
+    num_polys = len(polys)
+    es = [batch_open_kzg(p, [beta, (Fr.zero() - beta).sanitize(), beta.pow(2)], pk) for p in polys[: num_polys - 1]]
+    degree_proofs = [prove_degree_bound(p, pk, 2 ** (num_polys - i - 1)) for i, p in enumerate(polys)]
+    return ProofGemini(es, degree_proofs)
 
 
 # --- O(N) algebraic expected values for sizes the naive path cannot reach ---
@@ -585,3 +645,24 @@ def point_from_bytes(b: bytes):
     if b == bytes(64):
         return None
     return fe_from_bytes(b[:32]), fe_from_bytes(b[32:64])
+
+
+def expected_batch_open(coefs: Sequence[int], us: Sequence[int], alpha: int):
+    """(ys, W): the quotient of f by prod(x - u_i) is k successive synthetic divisions
+    (floor division composes); W = [q_k(alpha)]G."""
+    ys = [synthetic_division(coefs, u)[0] for u in us]
+    cur = list(coefs)
+    for u in us:
+        cur = synthetic_division(cur, u)[1] if len(cur) else []
+    qa = 0
+    for c in reversed(cur):
+        qa = (qa * alpha + c) % R_MOD
+    return ys, fast_mul(qa)
+
+
+def expected_degree_bound(coefs: Sequence[int], alpha: int, max_d: int, d: int):
+    """[f(alpha) * alpha^(max_d - d)]G."""
+    fa = 0
+    for c in reversed(coefs):
+        fa = (fa * alpha + c) % R_MOD
+    return fast_mul(fa * pow(alpha, max_d - d, R_MOD) % R_MOD)

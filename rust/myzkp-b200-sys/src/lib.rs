@@ -40,6 +40,10 @@ extern "C" {
                                   out: *mut u8) -> c_int;
     pub fn myzkp_gemini_fold_commit(ctx: *mut myzkp_ctx, coefs_le: *const u8, n_pow2: usize, rhos_le: *const u8,
                                     out: *mut u8, out_folds: *mut u8) -> c_int;
+    pub fn myzkp_kzg_batch_open(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, us_le: *const u8, k: usize,
+                                out_ys: *mut u8, out_w: *mut u8) -> c_int;
+    pub fn myzkp_kzg_prove_degree_bound(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, d: usize,
+                                        out_p: *mut u8) -> c_int;
     pub fn myzkp_fr_eval(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8) -> c_int;
     pub fn myzkp_fr_quotient(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8,
                              out_q: *mut u8) -> c_int;

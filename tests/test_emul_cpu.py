@@ -65,6 +65,9 @@ def test_field_ops(name, m):
     for x in vals[:24]:
         exp = (pow(x, -1, m) if x else 0) * RR % m
         assert u1("inv", x * RR % m) == exp
+        assert u1("inv_bingcd", x * RR % m) == exp
+    for x in [1, 2, m - 1, m - 2, (m + 1) // 2, 3, 1 << 200] + [rnd.randrange(1, m) for _ in range(300)]:
+        assert u1("inv_bingcd", x * RR % m) == pow(x, -1, m) * RR % m
 
 
 def test_group_law_special_cases():

@@ -26,6 +26,7 @@ def test_field_ops_random_and_edges(ctx, field, m):
         assert got == [fn(x, y) for x, y in zip(a, b)], f"op {op}"
     small = a[:256]
     assert _ints(ctx.test_field_op(field, 3, small)) == [pow(x, -1, m) if x else 0 for x in small]  # inverse(0)=0
+    assert _ints(ctx.test_field_op(field, 5, a[:2048])) == [pow(x, -1, m) if x else 0 for x in a[:2048]]  # binary GCD
     assert _ints(ctx.test_field_op(field, 4, small)) == [(-x) % m for x in small]
 
 

@@ -280,3 +280,39 @@ def test_heavy_buckets_hierarchical_merge(ctx):
                 assert ctx.commit(sc) == exp, (name, c, seg)
     finally:
         ctx.set_msm_params(0, 0)
+
+
+def test_batch_open_degree_bound_and_open_gemini(ctx):
+    """batch_open_kzg (kzg.rs:74-88), prove_degree_bound (kzg.rs:121-134),
+    open_gemini (gemini.rs:116-144) against the faithful oracle (small) and algebraic values (larger)."""
+    rnd = random.Random(77)
+    # the reference's test_gemini shape: 8 coefficients, SRS of 9 points, rho = (2,3,4), beta = 1234
+    alpha = rnd.randrange(R)
+    coefs = list(range(1, 9))
+    pk = mz.setup_kzg(mz.BN128.generator_g1(), None, 8, alpha=alpha, ctx=ctx)
+    opk = o.setup_kzg(o.generator_g1(), 8, alpha)
+    cms, polys = mz.split_and_fold_commit(coefs, [2, 3, 4], pk, want_folds=True)
+    all_polys = [mz.Polynomial(coefs)] + polys
+    proof = mz.open_gemini(all_polys, 1234, pk)
+    ofs = o.split_and_fold([Fr(c) for c in coefs], [Fr(2), Fr(3), Fr(4)])
+    oproof = o.open_gemini(ofs, Fr(1234), opk)
+    assert len(proof.es) == 3 and len(proof.degree_proofs) == 4
+    for e, oe in zip(proof.es, oproof.es):
+        assert e.ys == [y.sanitize().value for y in oe.ys]
+        assert e.w.as_tuple() == oe.w.affine_ints()
+    assert [p.as_tuple() for p in proof.degree_proofs] == [p.affine_ints() for p in oproof.degree_proofs]
+    with pytest.raises(RuntimeError):  # deg f > d
+        mz.prove_degree_bound(mz.Polynomial(coefs), pk, 3)
+    # larger, algebraic expected values
+    n = 3000
+    alpha = rnd.randrange(R)
+    ints = [rnd.randrange(R) for _ in range(n)]
+    ctx.srs_generate(alpha, n + 5)
+    us = [rnd.randrange(R) for _ in range(3)]
+    ys, w = ctx.batch_open(ints, us)
+    assert (ys, w) == o.expected_batch_open(ints, us, alpha)
+    ys1, w1 = ctx.batch_open(ints, us[:1])
+    assert (ys1[0], w1) == o.expected_open(ints, us[0], alpha)  # k = 1 is open_kzg
+    assert ctx.batch_open(ints[:2], us) == ([o.synthetic_division(ints[:2], u)[0] for u in us], None)
+    for d in (n - 1, n + 2, n + 4):
+        assert ctx.prove_degree_bound(ints, d) == o.expected_degree_bound(ints, alpha, n + 4, d)

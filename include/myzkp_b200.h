@@ -52,6 +52,10 @@ uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
  * other values fall back to automatic; entries per accumulate segment. */
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
 
+/* Batched-affine rounds in front of the XYZZ bucket accumulate (csrc/baa.cuh):
+ * -1 = automatic, 0 = off, r >= 1 = r pairing rounds. */
+int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds);
+
 /* Host-buffer commit/open upload a large polynomial in chunks on a copy stream while
  * earlier chunks are already being processed (each chunk is an MSM against its own SRS
  * range; the partial points are summed).  0 = automatic (1 below 2^23 coefficients,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "myzkp_last_error": (_c.c_char_p, [_vp]),
     "myzkp_kernel_launches": (_c.c_uint64, [_vp]),
     "myzkp_ctx_set_msm_params": (_i, [_vp, _i, _i]),
+    "myzkp_ctx_set_baa_rounds": (_i, [_vp, _i]),
     "myzkp_ctx_set_upload_chunks": (_i, [_vp, _i]),
     "myzkp_ctx_enable_phase_timing": (_i, [_vp, _i]),
     "myzkp_ctx_msm_phases": (_i, [_vp, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint64)]),

@@ -84,6 +84,9 @@ class Context:
     def set_msm_params(self, window_bits: int = 0, segment_len: int = 0):
         self._ck(self._lib.myzkp_ctx_set_msm_params(self.h, window_bits, segment_len))
 
+    def set_baa_rounds(self, rounds: int = -1):
+        self._ck(self._lib.myzkp_ctx_set_baa_rounds(self.h, rounds))
+
     def set_upload_chunks(self, chunks: int = 0):
         self._ck(self._lib.myzkp_ctx_set_upload_chunks(self.h, chunks))
 

@@ -106,7 +106,8 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   if (ctx->d_row_of_bit) cudaFree(ctx->d_row_of_bit);
   if (ctx->d_row_bits) cudaFree(ctx->d_row_bits);
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2, &ctx->red_a, &ctx->red_b,
+                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->red_a, &ctx->red_b,
                     &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
@@ -148,6 +149,12 @@ int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
   if (segment_len < 0 || segment_len > 65536) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bad segment_len");
   ctx->window_bits = window_bits;
   ctx->segment_len = segment_len;
+  return MYZKP_OK;
+}
+
+int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds) {
+  if (!ctx || rounds < -1 || rounds > 16) return MYZKP_ERR_INVALID_ARG;
+  ctx->baa_rounds = rounds;
   return MYZKP_OK;
 }
 

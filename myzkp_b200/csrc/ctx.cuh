@@ -79,6 +79,8 @@ struct myzkp_ctx {
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
   mz::DevBuf heads2;       // ping-pong levels of the head merge
+  mz::DevBuf baa_pts, baa_keys, baa_prefix, baa_meta;  // batched-affine rounds: private lists, prefixes, products
+  int baa_rounds = -1;     // -1 = automatic, 0 = off (XYZZ accumulate only)
   mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
@@ -137,6 +139,10 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 // XYZZ (device) -> canonical affine 64 B (device)
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
 int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);
+
+// ---- baa.cu ----
+int baa_accumulate(myzkp_ctx* ctx, const uint32_t* keys_s, const uint32_t* vals_s, uint64_t M, uint32_t L,
+                   uint32_t sentinel, int rounds, XYZZ* buckets, XYZZ* heads, uint32_t* head_keys, uint64_t T);
 
 // ---- sort.cu ----
 // LSD radix sort of (key, val) pairs by the low `bits` key bits; result in (*out_keys, *out_vals)

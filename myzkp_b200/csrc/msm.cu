@@ -362,10 +362,18 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
   MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(2);
-  msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-      keys_s, vals_s, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
-      ctx->head_keys.as<uint32_t>(), T);
-  MZ_LAUNCH_CHECK(ctx);
+  // batched-affine rounds pay off when runs are long enough to pair up (avg run >= 4)
+  int baa = ctx->baa_rounds;
+  if (baa < 0) baa = 0;  // automatic: off until measured faster on the target
+  if (baa > 0 && L >= 4) {
+    MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+                          ctx->head_keys.as<uint32_t>(), T));
+  } else {
+    msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+        keys_s, vals_s, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+        ctx->head_keys.as<uint32_t>(), T);
+    MZ_LAUNCH_CHECK(ctx);
+  }
 
   MZ_PHASE(3);
   // 4. merge segment heads, level by level (levels beyond the first are nearly empty

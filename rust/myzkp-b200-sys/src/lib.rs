@@ -22,6 +22,7 @@ extern "C" {
     pub fn myzkp_last_error(ctx: *const myzkp_ctx) -> *const c_char;
     pub fn myzkp_kernel_launches(ctx: *const myzkp_ctx) -> u64;
     pub fn myzkp_ctx_set_msm_params(ctx: *mut myzkp_ctx, window_bits: c_int, segment_len: c_int) -> c_int;
+    pub fn myzkp_ctx_set_baa_rounds(ctx: *mut myzkp_ctx, rounds: c_int) -> c_int;
     pub fn myzkp_ctx_set_upload_chunks(ctx: *mut myzkp_ctx, chunks: c_int) -> c_int;
     pub fn myzkp_ctx_enable_phase_timing(ctx: *mut myzkp_ctx, on: c_int) -> c_int;
     pub fn myzkp_ctx_msm_phases(ctx: *mut myzkp_ctx, back: c_int, out_ms: *mut f32, out_info: *mut u64) -> c_int;

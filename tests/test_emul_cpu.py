@@ -114,3 +114,44 @@ def test_group_law_special_cases():
         acc = xyzz(a)
         L.emul_g1_dbl(acc)
         assert to_aff(acc) == _fast_add(a, a)
+
+
+def test_batched_affine_rounds_emulated():
+    """The BAA per-thread bodies (csrc/baa.cuh) on the CPU: bucket sums for random sorted entry
+    lists incl. infinity points, duplicate points (doubling), P/-P pairs, odd runs, sentinels."""
+    L = _build("emul_baa")
+    rnd = random.Random(11)
+    base = [o.fast_mul(rnd.randrange(1, R)) for _ in range(10)]
+    table = base + [base[0], base[1], None, base[2], (base[3][0], P - base[3][1]), None]  # dup, inf, negation
+    def limbs(x):
+        return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    tb = []
+    for pt in table:
+        tb += ([0] * 16) if pt is None else (limbs(pt[0] * RR % P) + limbs(pt[1] * RR % P))
+    tbl = (ctypes.c_uint32 * len(tb))(*tb)
+    rinv = pow(RR, -1, P)
+    for trial in range(12):
+        nb = rnd.choice([1, 2, 5, 9])
+        m_valid = rnd.randrange(1, 90)
+        n_sent = rnd.randrange(0, 5)
+        ents = sorted((rnd.randrange(nb), rnd.randrange(len(table)) | (rnd.randrange(2) << 31)) for _ in range(m_valid))
+        if trial % 3 == 0:  # a long run of the same point, forces repeated doubling / cancellation
+            ents = sorted(ents + [(0, 10 | (rnd.randrange(2) << 31)) for _ in range(9)])
+        keys = [k for k, _ in ents] + [nb] * n_sent
+        vals = [v for _, v in ents] + [0] * n_sent
+        M = len(keys)
+        exp = [None] * nb
+        for k, v in ents:
+            pt = table[v & 0x7FFFFFFF]
+            if pt is not None and (v >> 31):
+                pt = (pt[0], (P - pt[1]) % P)
+            exp[k] = _fast_add(exp[k], pt)
+        for seg in (1, 2, 3, 7, 16, 200):
+            for rounds in (1, 2, 3, 8):
+                out = (ctypes.c_uint32 * (16 * nb))()
+                L.emul_baa_buckets((ctypes.c_uint32 * M)(*keys), (ctypes.c_uint32 * M)(*vals), M, seg, nb, tbl, rounds, nb, out)
+                got = []
+                for b in range(nb):
+                    x, y = fl(out, 16 * b) * rinv % P, fl(out, 16 * b + 8) * rinv % P
+                    got.append(None if (x, y) == (0, 0) else (x, y))
+                assert got == exp, (trial, seg, rounds)

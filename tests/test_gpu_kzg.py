@@ -316,3 +316,43 @@ def test_batch_open_degree_bound_and_open_gemini(ctx):
     assert ctx.batch_open(ints[:2], us) == ([o.synthetic_division(ints[:2], u)[0] for u in us], None)
     for d in (n - 1, n + 2, n + 4):
         assert ctx.prove_degree_bound(ints, d) == o.expected_degree_bound(ints, alpha, n + 4, d)
+
+
+def test_batched_affine_rounds_on_device(ctx):
+    """BAA rounds (csrc/baa.cu) against the XYZZ-only accumulate and the oracle, across windows,
+    segment lengths, round counts and scalar distributions (incl. duplicate / opposite SRS points)."""
+    n = 6000
+    alpha = 0x5A5A5A5A5A5A5A5A5A5A
+    ctx.srs_generate(alpha, n)
+    rnd = random.Random(4)
+    dists = {
+        "uniform": synth.limbs_to_ints(synth.random_scalars(n, 31)),
+        "bytes": [rnd.randrange(256) for _ in range(n)],
+        "all_one": [1] * n,
+        "zeros": [0 if rnd.random() < 0.3 else rnd.randrange(R) for _ in range(n)],
+    }
+    try:
+        for name, sc in dists.items():
+            exp = o.expected_commit(sc, alpha)
+            for rounds in (1, 2, 3, 6):
+                for c, seg in ((8, 0), (12, 5), (16, 0), (16, 64), (20, 0)):
+                    ctx.set_baa_rounds(rounds)
+                    ctx.set_msm_params(c, seg)
+                    assert ctx.commit(sc) == exp, (name, rounds, c, seg)
+        # explicit SRS with repeated points, P / -P and infinity: doubling and cancellation inside a batch
+        base = [o.fast_mul(k) for k in (3, 5, 7)]
+        neg = lambda p: (p[0], o.P_MOD - p[1])
+        pts = [base[0]] * 6 + [neg(base[0])] * 3 + [None, base[1], base[1], neg(base[1]), base[2]] * 2
+        ctx.srs_load(pts)
+        sc = [1] * len(pts)
+        exp = None
+        for p_ in pts:
+            exp = o._fast_add(exp, p_)
+        for rounds in (1, 2, 4):
+            ctx.set_baa_rounds(rounds)
+            for c, seg in ((8, 0), (8, 4), (16, 3)):
+                ctx.set_msm_params(c, seg)
+                assert ctx.commit(sc) == exp, (rounds, c, seg)
+    finally:
+        ctx.set_baa_rounds(-1)
+        ctx.set_msm_params(0, 0)

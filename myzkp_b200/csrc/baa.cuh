@@ -9,7 +9,13 @@
 //     invert   : one batched inversion over the per-thread products (separate kernel)
 //     backward : per thread, finish every pair with its denominator inverse
 // Each round halves the runs; after a few rounds the leftover list is finished by the
-// serial XYZZ pass.  Group-law special cases are kept (curve.rs:131-145): infinity
+// serial XYZZ pass.
+//
+// STATUS (round 1, measured on B200, profiles/baa_r1.md): bit-exact, but only break-even
+// with the plain XYZZ accumulate (round 0 is HBM-bound: two passes x two 128-byte random
+// gathers per addition, plus a separate inversion kernel per round), so it is OFF by
+// default (myzkp_ctx_set_baa_rounds).  A fused per-thread variant with in-thread
+// branch-free inversions was measured 1.5x slower and removed.  Group-law special cases are kept (curve.rs:131-145): infinity
 // operands, P + P (the doubling slope 3x^2 / 2y goes through the same batch) and
 // P + (-P).
 //
@@ -22,18 +28,22 @@
 namespace mz {
 
 // item source of one thread in one round
+// Item i of a thread lives at base[i * stride]: the kernels interleave the threads
+// (stride = number of threads) so that a warp walking its lists in step touches
+// consecutive addresses; the CPU emulation uses stride 1.
 struct BaaSrc {
-  // round 0: sorted entries + resident table
+  // round 0: (transposed) sorted entries + resident table
   const uint32_t* keys_s;   // thread's first sorted key
   const uint32_t* vals_s;   // thread's first sorted val (sign << 31 | table index)
   const Affine* tbl;
   // rounds >= 1: the thread's private list
   const Affine* pts;
   const uint32_t* keys;
+  size_t stride;
 };
 
 template <bool R0>
-MZ_HD uint32_t baa_key(const BaaSrc& s, uint32_t i) { return R0 ? s.keys_s[i] : s.keys[i]; }
+MZ_HD uint32_t baa_key(const BaaSrc& s, uint32_t i) { return R0 ? s.keys_s[i * s.stride] : s.keys[i * s.stride]; }
 
 MZ_HD Fq baa_load_fq(const Fq* p) {
   Fq r;
@@ -59,16 +69,16 @@ MZ_HD void baa_store_fq(Fq* p, const Fq& r) {
 
 template <bool R0>
 MZ_HD Fq baa_x(const BaaSrc& s, uint32_t i) {
-  return baa_load_fq(R0 ? &s.tbl[s.vals_s[i] & 0x7fffffffu].x : &s.pts[i].x);
+  return baa_load_fq(R0 ? &s.tbl[s.vals_s[i * s.stride] & 0x7fffffffu].x : &s.pts[i * s.stride].x);
 }
 template <bool R0>
 MZ_HD Fq baa_y(const BaaSrc& s, uint32_t i) {
   if (R0) {
-    uint32_t v = s.vals_s[i];
+    uint32_t v = s.vals_s[i * s.stride];
     Fq y = baa_load_fq(&s.tbl[v & 0x7fffffffu].y);
     return (v >> 31) ? fe_neg(y) : y;
   }
-  return baa_load_fq(&s.pts[i].y);
+  return baa_load_fq(&s.pts[i * s.stride].y);
 }
 
 // Denominator of the pair (a, b) = (item i, item i+1):
@@ -91,59 +101,52 @@ MZ_HD int baa_classify(const BaaSrc& s, uint32_t i, const Fq& xa, const Fq& xb, 
 }
 
 // number of non-sentinel entries at the head of a round-0 segment of length len
-MZ_HD uint32_t baa_count_valid(const uint32_t* keys_s, uint32_t len, uint32_t sentinel) {
+MZ_HD uint32_t baa_count_valid(const uint32_t* keys_s, size_t stride, uint32_t len, uint32_t sentinel) {
   uint32_t n = 0;
-  while (n < len && keys_s[n] < sentinel) n++;
+  while (n < len && keys_s[n * stride] < sentinel) n++;
   return n;
 }
 
-// Forward pass: right-to-left greedy pairing inside runs; prefix[j] = d_0 * ... * d_j in
-// pairing order.  Returns the number of pairs; prod = product of all denominators (one if none).
-// prefix element j lives at prefix[j * pstride] (the kernels interleave threads so that a
-// warp's accesses to the same j coalesce).
+// Pairing: the thread's list is cut into fixed slots (0,1), (2,3), ...; a slot is a pair
+// when both items exist and share the bucket key, otherwise its items pass through.  No
+// look-ahead is needed and the lanes of a warp stay in step slot by slot, whatever their
+// run boundaries are.
+//
+// Forward pass: slots right to left; prefix[j] = d_0 * ... * d_j in that order.  Returns the
+// number of pairs; prod = product of all denominators (one if none).  Prefix element j lives
+// at prefix[j * pstride] (the kernels interleave threads so a warp's accesses coalesce).
+// Both passes work on a slot range [q0, q1) of the thread's list.
 template <bool R0>
-MZ_HD uint32_t baa_forward(const BaaSrc& s, uint32_t n, Fq* prefix, size_t pstride, Fq& prod) {
+MZ_HD uint32_t baa_forward(const BaaSrc& s, uint32_t n, uint32_t q0, uint32_t q1, Fq* prefix, size_t pstride, Fq& prod) {
   uint32_t cnt = 0;
   prod = Fq::one();
-  int64_t i = (int64_t)n - 1;
-  while (i >= 1) {
-    if (baa_key<R0>(s, (uint32_t)i - 1) == baa_key<R0>(s, (uint32_t)i)) {
-      Fq xa = baa_x<R0>(s, (uint32_t)i - 1), xb = baa_x<R0>(s, (uint32_t)i);
+  if (q1 > n / 2) q1 = n / 2;  // a trailing single item is never a pair
+  for (int64_t q = (int64_t)q1 - 1; q >= (int64_t)q0; q--) {
+    const uint32_t i = 2 * (uint32_t)q;
+    if (baa_key<R0>(s, i) == baa_key<R0>(s, i + 1)) {
+      Fq xa = baa_x<R0>(s, i), xb = baa_x<R0>(s, i + 1);
       Fq d;
-      baa_classify<R0>(s, (uint32_t)i - 1, xa, xb, d);
+      baa_classify<R0>(s, i, xa, xb, d);
       prod = cnt ? fe_mul(prod, d) : d;
       baa_store_fq(prefix + (size_t)cnt * pstride, prod);
       cnt++;
-      i -= 2;
-    } else {
-      i -= 1;
     }
   }
   return cnt;
 }
 
-// Backward pass: left-to-right over the same pairing (pairs are met in reverse pairing
-// order), writing the next list (dst may alias the private source list: o <= i always).
+// Backward pass: slots left to right (pairs are met in reverse forward order), writing the
+// next list with the source's stride (dst may alias the private source list: o <= i always).
 // inv = inverse of prod.  Returns the new item count.
 template <bool R0>
-MZ_HD uint32_t baa_backward(const BaaSrc& s, uint32_t n, const Fq* prefix, size_t pstride, Fq inv, uint32_t cnt,
-                            Affine* dst_pts, uint32_t* dst_keys) {
-  uint32_t j = cnt, o = 0, i = 0;
-  while (i < n) {
+MZ_HD uint32_t baa_backward(const BaaSrc& s, uint32_t n, uint32_t q0, uint32_t q1, const Fq* prefix, size_t pstride,
+                            Fq inv, uint32_t cnt, Affine* dst_pts, uint32_t* dst_keys, uint32_t o) {
+  uint32_t j = cnt;
+  for (uint32_t i = 2 * q0; i < n && i < 2 * q1; i += 2) {
     const uint32_t k = baa_key<R0>(s, i);
-    uint32_t e = i + 1;
-    while (e < n && baa_key<R0>(s, e) == k) e++;
-    if ((e - i) & 1u) {  // odd run: its leftmost item passes through
-      Affine p;
-      p.x = baa_x<R0>(s, i);
-      p.y = baa_y<R0>(s, i);
-      baa_store_fq(&dst_pts[o].x, p.x);
-      baa_store_fq(&dst_pts[o].y, p.y);
-      dst_keys[o] = k;
-      o++;
-      i++;
-    }
-    for (; i < e; i += 2) {
+    const bool has_b = i + 1 < n;
+    const uint32_t kb = has_b ? baa_key<R0>(s, i + 1) : 0;
+    if (has_b && kb == k) {
       j--;
       Fq xa = baa_x<R0>(s, i), xb = baa_x<R0>(s, i + 1);
       Fq d;
@@ -172,10 +175,27 @@ MZ_HD uint32_t baa_backward(const BaaSrc& s, uint32_t n, const Fq* prefix, size_
         r.x = Fq::zero();
         r.y = Fq::zero();
       }
-      baa_store_fq(&dst_pts[o].x, r.x);
-      baa_store_fq(&dst_pts[o].y, r.y);
-      dst_keys[o] = k;
+      baa_store_fq(&dst_pts[o * s.stride].x, r.x);
+      baa_store_fq(&dst_pts[o * s.stride].y, r.y);
+      dst_keys[o * s.stride] = k;
       o++;
+    } else {  // pass through (read both before writing: o may equal i)
+      Fq ax = baa_x<R0>(s, i), ay = baa_y<R0>(s, i);
+      Fq bx = ax, by = ay;
+      if (has_b) {
+        bx = baa_x<R0>(s, i + 1);
+        by = baa_y<R0>(s, i + 1);
+      }
+      baa_store_fq(&dst_pts[o * s.stride].x, ax);
+      baa_store_fq(&dst_pts[o * s.stride].y, ay);
+      dst_keys[o * s.stride] = k;
+      o++;
+      if (has_b) {
+        baa_store_fq(&dst_pts[o * s.stride].x, bx);
+        baa_store_fq(&dst_pts[o * s.stride].y, by);
+        dst_keys[o * s.stride] = kb;
+        o++;
+      }
     }
   }
   return o;
@@ -184,8 +204,8 @@ MZ_HD uint32_t baa_backward(const BaaSrc& s, uint32_t n, const Fq* prefix, size_
 // Finish: serial XYZZ pass over the thread's private list.  Same contract as
 // msm_accumulate: the first run goes to *head (key in *head_key), later runs are the
 // unique first writers of their buckets.
-MZ_HD void baa_finish(const Affine* pts, const uint32_t* keys, uint32_t n, uint32_t sentinel, XYZZ* buckets, XYZZ* head,
-                      uint32_t* head_key) {
+MZ_HD void baa_finish(const Affine* pts, const uint32_t* keys, size_t stride, uint32_t n, uint32_t sentinel,
+                      XYZZ* buckets, XYZZ* head, uint32_t* head_key) {
   if (n == 0) {
     *head_key = sentinel;
     return;
@@ -196,10 +216,10 @@ MZ_HD void baa_finish(const Affine* pts, const uint32_t* keys, uint32_t n, uint3
   bool first_run = true;
   for (uint32_t i = 0; i < n; i++) {
     Affine p;
-    p.x = baa_load_fq(&pts[i].x);
-    p.y = baa_load_fq(&pts[i].y);
+    p.x = baa_load_fq(&pts[i * stride].x);
+    p.y = baa_load_fq(&pts[i * stride].y);
     xyzz_madd(acc, p);
-    uint32_t k_next = (i + 1 < n) ? keys[i + 1] : sentinel;
+    uint32_t k_next = (i + 1 < n) ? keys[(i + 1) * stride] : sentinel;
     if (k_next != cur) {
       if (first_run) *head = acc;
       else buckets[cur] = acc;

@@ -88,6 +88,8 @@ int myzkp_ctx_create(myzkp_ctx** out, int device_id) {
   ctx->device = device_id;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  // the MSM gathers 64-byte points at random: do not let L2 over-fetch whole 128-byte lines
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return MYZKP_ERR_CUDA;
@@ -107,7 +109,7 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   if (ctx->d_row_bits) cudaFree(ctx->d_row_bits);
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                     &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
-                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->red_a, &ctx->red_b,
+                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans, &ctx->red_a, &ctx->red_b,
                     &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)

@@ -79,7 +79,7 @@ struct myzkp_ctx {
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
   mz::DevBuf heads2;       // ping-pong levels of the head merge
-  mz::DevBuf baa_pts, baa_keys, baa_prefix, baa_meta;  // batched-affine rounds: private lists, prefixes, products
+  mz::DevBuf baa_pts, baa_keys, baa_prefix, baa_meta, baa_trans;  // batched-affine rounds: private lists, prefixes, products
   int baa_rounds = -1;     // -1 = automatic, 0 = off (XYZZ accumulate only)
   mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan

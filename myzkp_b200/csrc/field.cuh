@@ -373,13 +373,11 @@ MZ_HD void limbs_shr1(uint32_t* a, uint32_t top) {  // a = (top:a) >> 1
 // x = x/2 mod m for x in [0, m)
 template <class PR>
 MZ_HD void limbs_half_mod(uint32_t* x) {
-  uint32_t carry = 0;
-  if (x[0] & 1u) {
-    x[0] = add_cc(x[0], mod_limb<PR>(0));
+  const uint32_t odd = 0u - (x[0] & 1u);
+  x[0] = add_cc(x[0], mod_limb<PR>(0) & odd);
 #pragma unroll
-    for (int i = 1; i < 8; i++) x[i] = addc_cc(x[i], mod_limb<PR>(i));
-    carry = addc(0, 0);
-  }
+  for (int i = 1; i < 8; i++) x[i] = addc_cc(x[i], mod_limb<PR>(i) & odd);
+  const uint32_t carry = addc(0, 0);
   limbs_shr1(x, carry);
 }
 MZ_HD bool limbs_geq(const uint32_t* a, const uint32_t* b) {  // a >= b

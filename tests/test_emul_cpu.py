@@ -70,6 +70,7 @@ def test_field_ops(name, m):
         assert u1("inv_bingcd", x * RR % m) == pow(x, -1, m) * RR % m
 
 
+
 def test_group_law_special_cases():
     L = _build("emul_g1")
     rnd = random.Random(7)
@@ -132,7 +133,7 @@ def test_batched_affine_rounds_emulated():
     rinv = pow(RR, -1, P)
     for trial in range(12):
         nb = rnd.choice([1, 2, 5, 9])
-        m_valid = rnd.randrange(1, 90)
+        m_valid = rnd.randrange(1, 90) if trial != 5 else 330  # trial 5 spans several in-thread batches
         n_sent = rnd.randrange(0, 5)
         ents = sorted((rnd.randrange(nb), rnd.randrange(len(table)) | (rnd.randrange(2) << 31)) for _ in range(m_valid))
         if trial % 3 == 0:  # a long run of the same point, forces repeated doubling / cancellation
@@ -146,12 +147,12 @@ def test_batched_affine_rounds_emulated():
             if pt is not None and (v >> 31):
                 pt = (pt[0], (P - pt[1]) % P)
             exp[k] = _fast_add(exp[k], pt)
-        for seg in (1, 2, 3, 7, 16, 200):
-            for rounds in (1, 2, 3, 8):
+        for seg in (1, 2, 3, 7, 16, 200, 400):
+            for rounds, fused in ((1, 0), (2, 0), (3, 0), (8, 0)):
                 out = (ctypes.c_uint32 * (16 * nb))()
-                L.emul_baa_buckets((ctypes.c_uint32 * M)(*keys), (ctypes.c_uint32 * M)(*vals), M, seg, nb, tbl, rounds, nb, out)
+                L.emul_baa_buckets((ctypes.c_uint32 * M)(*keys), (ctypes.c_uint32 * M)(*vals), M, seg, nb, tbl, rounds, nb, out, fused)
                 got = []
                 for b in range(nb):
                     x, y = fl(out, 16 * b) * rinv % P, fl(out, 16 * b + 8) * rinv % P
                     got.append(None if (x, y) == (0, 0) else (x, y))
-                assert got == exp, (trial, seg, rounds)
+                assert got == exp, (trial, seg, rounds, fused)

@@ -343,7 +343,7 @@ def main():
             "config": {
                 "workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
                 "points_total": n_total, "points_per_gpu": n_local, "parallelism": f"range-sharded x{world}",
-                "l2": "inputs larger than L2 (scalars %d MiB + SRS table %d MiB per GPU; no flush needed)"
+                "l2": "inputs larger than L2 (scalars %d MiB + resident SRS table of 2^(b_j) multiples, >= %d MiB per GPU; no flush needed)"
                       % (n_local * 32 >> 20, n_local * 64 * 32 >> 20),
                 "window_bits": info.get("window_bits"), "srs_setup_s": t_srs,
             },

@@ -111,16 +111,30 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
   h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+  // all loads first (16-byte vectors, order inside the tile is irrelevant for counting),
+  // then the shared-memory atomics: keeps 4 independent loads per thread in flight
+  uint32_t k[kSortItems];
+  if (base + kSortTile <= n) {
+    const uint4* src = reinterpret_cast<const uint4*>(keys + base);
 #pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1u);
+    for (int i = 0; i < kSortItems / 4; i++) {
+      uint4 q = __ldg(src + i * kSortThreads + threadIdx.x);
+      k[4 * i] = q.x; k[4 * i + 1] = q.y; k[4 * i + 2] = q.z; k[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) atomicAdd(&h[(k[i] >> shift) & (kRadix - 1)], 1u);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
+      if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1u);
+    }
   }
   __syncthreads();
   hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, 4)
     sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
                       const uint32_t* __restrict__ hist_scanned, uint32_t ntiles, uint32_t* __restrict__ keys_out,
                       uint32_t* __restrict__ vals_out) {
@@ -139,14 +153,17 @@ __global__ void __launch_bounds__(kSortThreads, 3)
   __syncthreads();
 
   // warp-blocked arrangement: warp w owns tile entries [w*512, (w+1)*512) in index order
-  uint32_t k[kSortItems], v[kSortItems], rank[kSortItems];
+  uint32_t k[kSortItems], rank[kSortItems];
   const uint32_t wbase = (uint32_t)w * (32 * kSortItems);
 #pragma unroll
   for (int i = 0; i < kSortItems; i++) {
     uint32_t p = wbase + i * 32 + lane;
+    k[i] = p < tile_n ? keys_in[tile_base + p] : 0xffffffffu;
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = wbase + i * 32 + lane;
     bool ok = p < tile_n;
-    k[i] = ok ? keys_in[tile_base + p] : 0xffffffffu;
-    v[i] = ok ? vals_in[tile_base + p] : 0u;
     uint32_t d = ok ? ((k[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // 256 = padding, never matches a digit
     // peers: lanes of this warp holding the same digit in this round
     uint32_t peers = __match_any_sync(0xffffffffu, d);
@@ -159,6 +176,13 @@ __global__ void __launch_bounds__(kSortThreads, 3)
     prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
     rank[i] = prev + before;
     __syncwarp();
+  }
+  // the values are only needed for the placement: fetch them while the digit scan runs
+  uint32_t v[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = wbase + i * 32 + lane;
+    v[i] = p < tile_n ? vals_in[tile_base + p] : 0u;
   }
   __syncthreads();
   // digit totals -> exclusive scan over digits -> per-warp bases

@@ -113,6 +113,13 @@ int myzkp_kzg_batch_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, cons
  * f against the SRS window starting at max_d - d (max_d = srs_len - 1).  deg f > d is
  * an error (the reference index-panics). */
 int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, size_t d, uint8_t out_p[64]);
+/* G1 MSM sum_i scalars[i] * points[i].  points == NULL: against the resident SRS (same as
+ * myzkp_kzg_commit).  Otherwise n caller-supplied affine points (the
+ * accumulate_curve_points / eval_with_powers_on_curve call sites outside KZG,
+ * zksnark/utils.rs:83-93): a temporary table is built for them per call (about 15x the
+ * cost of the MSM itself - meant for correctness and moderate sizes, not the hot path). */
+int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_or_null /* n*64 */, size_t n,
+                 uint8_t out[64]);
 /* Polynomial::eval (polynomial.rs:120-128). */
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]);
 /* y and the quotient coefficients themselves (n-1 of them; n >= 1). */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "myzkp_gemini_fold_commit": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_kzg_batch_open": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "myzkp_kzg_prove_degree_bound": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "myzkp_g1_msm": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "myzkp_fr_eval": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "myzkp_fr_quotient": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_kzg_commit_dev": (_i, [_vp, _vp, _sz, _vp]),

@@ -175,6 +175,18 @@ class Context:
         self._ck(self._lib.myzkp_kzg_prove_degree_bound(self.h, _ptr(a), a.shape[0], d, _ptr(out)))
         return point_from_bytes(out)
 
+    def g1_msm(self, scalars, points=None):
+        """sum_i scalars[i] * points[i]; points None = the resident SRS."""
+        a = scalars_to_bytes(scalars)
+        pb = None
+        if points is not None:
+            pb = np.frombuffer(b"".join(point_to_bytes(p) for p in points), dtype=np.uint8).reshape(-1, 64).copy()
+            if pb.shape[0] != a.shape[0]:
+                raise ValueError("scalars and points differ in length")
+        out = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_g1_msm(self.h, _ptr(a), _ptr(pb) if pb is not None else None, a.shape[0], _ptr(out)))
+        return point_from_bytes(out)
+
     def fr_eval(self, coefs, u: int) -> int:
         a = scalars_to_bytes(coefs)
         ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()

@@ -438,6 +438,44 @@ int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t
   return end_call_check_flag(ctx);
 }
 
+int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_or_null, size_t n, uint8_t out[64]) {
+  if (!ctx || (!scalars_le && n) || !out) return MYZKP_ERR_INVALID_ARG;
+  if (!points_or_null) return myzkp_kzg_commit(ctx, scalars_le, n, out);  // against the resident SRS
+  if (n == 0) {
+    memset(out, 0, 64);
+    return MYZKP_OK;
+  }
+  // caller-supplied points (accumulate_curve_points-style call sites, zksnark/utils.rs:83-93): the resident
+  // table is set aside, a temporary table is built for these points, and the same pipeline runs
+  Affine* saved_table = ctx->table;
+  const size_t saved_n = ctx->srs_n;
+  const int saved_rows = ctx->table_rows;
+  const uint32_t saved_windows = ctx->windows;
+  int saved_row_bits[mz::kMaxTableRows];
+  uint8_t saved_row_of_bit[256];
+  memcpy(saved_row_bits, ctx->row_bits, sizeof saved_row_bits);
+  memcpy(saved_row_of_bit, ctx->row_of_bit, sizeof saved_row_of_bit);
+  ctx->table = nullptr;
+  ctx->srs_n = 0;
+  int rc = myzkp_srs_load_g1(ctx, points_or_null, n);
+  if (rc == MYZKP_OK) rc = myzkp_kzg_commit(ctx, scalars_le, n, out);
+  std::string err = ctx->err;
+  if (ctx->table) cudaFree(ctx->table);
+  ctx->table = saved_table;
+  ctx->srs_n = saved_n;
+  ctx->table_rows = saved_rows;
+  ctx->windows = saved_windows;
+  memcpy(ctx->row_bits, saved_row_bits, sizeof saved_row_bits);
+  memcpy(ctx->row_of_bit, saved_row_of_bit, sizeof saved_row_of_bit);
+  if (ctx->d_row_of_bit) {
+    cudaMemcpyAsync(ctx->d_row_of_bit, ctx->row_of_bit, 256, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_row_bits, ctx->row_bits, sizeof(int) * mz::kMaxTableRows, cudaMemcpyHostToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  ctx->err = err;
+  return rc;
+}
+
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]) {
   if (!ctx || (!coefs_le && n) || !u_le || !out_y) return MYZKP_ERR_INVALID_ARG;
   if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");

@@ -160,13 +160,20 @@ __global__ void __launch_bounds__(kSortThreads, 4)
     uint32_t p = wbase + i * 32 + lane;
     k[i] = p < tile_n ? keys_in[tile_base + p] : 0xffffffffu;
   }
+  // all 16 matches first (they only depend on the keys, so they pipeline), then the
+  // sequential per-warp counter updates
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    uint32_t p = wbase + i * 32 + lane;
+    uint32_t d = p < tile_n ? ((k[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // 256 = padding, never a digit
+    rank[i] = __match_any_sync(0xffffffffu, d);  // peers: lanes of this warp with the same digit in this round
+  }
 #pragma unroll
   for (int i = 0; i < kSortItems; i++) {
     uint32_t p = wbase + i * 32 + lane;
     bool ok = p < tile_n;
-    uint32_t d = ok ? ((k[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // 256 = padding, never matches a digit
-    // peers: lanes of this warp holding the same digit in this round
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t d = (k[i] >> shift) & (kRadix - 1);
+    uint32_t peers = rank[i];
     uint32_t before = __popc(peers & ((1u << lane) - 1u));
     uint32_t prev = 0;
     if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter

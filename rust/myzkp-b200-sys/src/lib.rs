@@ -45,6 +45,8 @@ extern "C" {
                                 out_ys: *mut u8, out_w: *mut u8) -> c_int;
     pub fn myzkp_kzg_prove_degree_bound(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, d: usize,
                                         out_p: *mut u8) -> c_int;
+    pub fn myzkp_g1_msm(ctx: *mut myzkp_ctx, scalars_le: *const u8, points_or_null: *const u8, n: usize,
+                        out: *mut u8) -> c_int;
     pub fn myzkp_fr_eval(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8) -> c_int;
     pub fn myzkp_fr_quotient(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8,
                              out_q: *mut u8) -> c_int;

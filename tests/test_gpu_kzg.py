@@ -356,3 +356,25 @@ def test_batched_affine_rounds_on_device(ctx):
     finally:
         ctx.set_baa_rounds(-1)
         ctx.set_msm_params(0, 0)
+
+
+def test_generic_msm_with_caller_points(ctx):
+    """myzkp_g1_msm with caller-supplied points (accumulate_curve_points call sites, zksnark/utils.rs:83-93);
+    the resident SRS must survive the call."""
+    rnd = random.Random(12)
+    alpha = 987654321
+    ctx.srs_generate(alpha, 64)
+    ks = [rnd.randrange(1, R) for _ in range(300)]
+    pts = [o.fast_mul(k) for k in ks[:40]] * 7 + [None] * 20  # repeats and infinities
+    sc = [rnd.randrange(R) for _ in pts]
+    exp_k = sum(s * ks[i % 40] for i, s in enumerate(sc[:280])) % R
+    assert ctx.g1_msm(sc, pts) == o.fast_mul(exp_k)
+    # the faithful naive MSM of the reference on a small case
+    small_pts, small_sc = pts[:12], sc[:12]
+    opk = o.PublicKeyKZG([o.G1Point.new(o.Fq(x), o.Fq(y)) for x, y in small_pts])
+    assert ctx.g1_msm(small_sc, small_pts) == o.commit_kzg(o.Polynomial([Fr(c) for c in small_sc]), opk).affine_ints()
+    assert ctx.g1_msm([], []) is None
+    # resident SRS intact
+    coefs = [rnd.randrange(R) for _ in range(64)]
+    assert ctx.srs_len == 64
+    assert ctx.g1_msm(coefs) == o.expected_commit(coefs, alpha) == ctx.commit(coefs)

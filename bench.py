@@ -394,6 +394,22 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
         ex[f"commit_2^{lg}_ms"] = ms_c
         ex[f"open_2^{lg}_ms"] = ms_o
         ex[f"commit_2^{lg}_points_per_s"] = n / (ms_c * 1e-3)
+    # HBM-bound scalar-field phases of open (64 B per coefficient algorithmic)
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    n = 1 << log2n
+    sc = torch.from_numpy(synth.random_scalars(n, synth.SEED_SCALARS + log2n).view(np.int64).reshape(-1)).to(dev)
+    q = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    c0 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    ms_q = timeit(lambda: ctx.fr_range_quotient_dev(sc.data_ptr(), n, u, 0, q.data_ptr(), c0.data_ptr()))
+    gbs = n * 64 / (ms_q * 1e-3) / 1e9
+    ex[f"quotient_scan_2^{log2n}_ms"] = ms_q
+    ex["quotient_scan_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                    "frac": (gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                    "note": "algorithmic 64 B/coefficient (read f, write q); the 3-kernel form moves 96 B"}
+    del sc, q
     if log2n >= 20:
         n = 1 << 20
         coefs = synth.random_scalars(n, synth.SEED_GEMINI_COEF)

@@ -74,6 +74,48 @@ int end_call_check_flag(myzkp_ctx* ctx) {
   return MYZKP_OK;
 }
 
+// MSM of n scalars that arrive in K upload chunks (events ctx->copy_ev[k]).  With u_le != NULL the
+// scalars are the quotient of the uploaded polynomial by (x - u): chunks are then consumed top first,
+// the scan carry stays on the device, and y is left at kSmallY.
+int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descending, const uint8_t* u_le,
+                uint32_t* d_quot, XYZZ* d_res) {
+  uint8_t* s = ctx->small.as<uint8_t>();
+  uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallY);  // carry chain, ends as y
+  uint32_t* c0_prev = reinterpret_cast<uint32_t*>(s + kSmallY + 32);
+  int* flag = reinterpret_cast<int*>(s + kSmallFlag);
+  const size_t n_msm = u_le ? n - 1 : n;  // the quotient has one coefficient less
+  const int c = msm_pick_window(ctx, n_msm);
+  const size_t nb = (size_t)1 << (c - 1);
+  MZ_CUDA_TRY(ctx, ctx->buckets.ensure(2 * nb * sizeof(XYZZ)));
+  XYZZ* b0 = ctx->buckets.as<XYZZ>();
+  XYZZ* b1 = b0 + nb;
+  const size_t per = (n + K - 1) / K;
+  bool first = true;
+  for (int i = 0; i < K; i++) {
+    const int k = descending ? K - 1 - i : i;
+    size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+    if (lo >= hi) continue;
+    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+    const uint32_t* sc = d_coefs + lo * 8;
+    size_t len = hi - lo;
+    if (u_le) {
+      MZ_TRY(fr_check_canonical(ctx, sc, len, flag));
+      const bool top = (hi == n);
+      if (!top) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(c0_prev, c0, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+      MZ_TRY(fr_range_quotient(ctx, sc, len, u_le, nullptr, d_quot + lo * 8, c0, top ? nullptr : c0_prev));
+      // q[i] = q_{lo+i} pairs with SRS point lo+i; the global top coefficient q_{n-1} is the zero carry
+      sc = d_quot + lo * 8;
+      if (top) len -= 1;
+    }
+    if (len == 0) continue;
+    MZ_TRY(msm_fill_buckets(ctx, sc, len, lo, c, first ? b0 : b1));
+    if (!first) MZ_TRY(msm_add_buckets(ctx, b0, b1, c));
+    first = false;
+  }
+  if (first) MZ_CUDA_TRY(ctx, cudaMemsetAsync(b0, 0, nb * sizeof(XYZZ), ctx->stream));
+  return msm_reduce_buckets(ctx, c, b0, d_res);
+}
+
 }  // namespace
 
 extern "C" {
@@ -273,16 +315,12 @@ int myzkp_kzg_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, uint8_t 
     if (n) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     MZ_TRY(myzkp_kzg_commit_dev(ctx, ctx->scalars.p, n, s + kSmallPoint));
   } else {
-    // chunk k is committed (against SRS points [lo_k, hi_k)) while chunk k+1 is still on the bus
+    // chunk k is accumulated (against SRS points [lo_k, hi_k)) while chunk k+1 is still on the bus;
+    // all chunks use the window of the whole polynomial and share one final bucket reduce
     MZ_TRY(enqueue_chunk_uploads(ctx, coefs_le, ctx->scalars.as<uint8_t>(), n, K, false));
     XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
-    const size_t per = (n + K - 1) / K;
-    for (int k = 0; k < K; k++) {
-      size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
-      MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
-      MZ_TRY(msm_xyzz(ctx, ctx->scalars.as<uint32_t>() + lo * 8, hi > lo ? hi - lo : 0, lo, res + k));
-    }
-    MZ_TRY(sum_partials(ctx, res, (size_t)K, s + kSmallPoint));
+    MZ_TRY(chunked_msm(ctx, ctx->scalars.as<uint32_t>(), n, K, /*descending=*/false, nullptr, nullptr, res));
+    MZ_TRY(xyzz_to_bytes(ctx, res, 1, s + kSmallPoint));
   }
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_c, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
   return end_call_check_flag(ctx);
@@ -307,24 +345,8 @@ int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint
     MZ_TRY(enqueue_chunk_uploads(ctx, coefs_le, ctx->scalars.as<uint8_t>(), n, K, true));
     MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
     XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
-    uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallY);          // carry chain, ends as y
-    uint32_t* c0_prev = reinterpret_cast<uint32_t*>(s + kSmallY + 32);
-    int* flag = reinterpret_cast<int*>(s + kSmallFlag);
-    const size_t per = (n + K - 1) / K;
-    for (int k = K - 1; k >= 0; k--) {
-      size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
-      if (lo >= hi) continue;
-      MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
-      const uint32_t* coefs = ctx->scalars.as<uint32_t>() + lo * 8;
-      uint32_t* q = ctx->scalars2.as<uint32_t>() + lo * 8;
-      MZ_TRY(fr_check_canonical(ctx, coefs, hi - lo, flag));
-      const bool top = (hi == n);
-      if (!top) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(c0_prev, c0, 32, cudaMemcpyDeviceToDevice, ctx->stream));
-      MZ_TRY(fr_range_quotient(ctx, coefs, hi - lo, u_le, nullptr, q, c0, top ? nullptr : c0_prev));
-      // q[i] = q_{lo+i} pairs with SRS point lo+i; the global top coefficient q_{n-1} is the zero carry
-      MZ_TRY(msm_xyzz(ctx, q, top ? hi - lo - 1 : hi - lo, lo, res + k));
-    }
-    MZ_TRY(sum_partials(ctx, res, (size_t)K, s + kSmallPoint));
+    MZ_TRY(chunked_msm(ctx, ctx->scalars.as<uint32_t>(), n, K, /*descending=*/true, u_le, ctx->scalars2.as<uint32_t>(), res));
+    MZ_TRY(xyzz_to_bytes(ctx, res, 1, s + kSmallPoint));
   }
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_w, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));

@@ -99,6 +99,7 @@ struct myzkp_ctx {
   bool phase_timing = false;
   cudaEvent_t phase_ev[kPhaseSlots][6] = {};
   bool phase_valid[kPhaseSlots] = {};
+  bool phase_pending = false;  // fill_buckets recorded events 0-4 of the current slot
   uint64_t msm_count = 0;  // MSMs run so far (slot = count % kPhaseSlots)
   // facts about each MSM: window bits, windows, entries, segment length, segments, buckets
   uint64_t msm_info[kPhaseSlots][6] = {};
@@ -136,6 +137,12 @@ inline int fail(myzkp_ctx* ctx, int code, const char* msg) {
 // MSM of n canonical scalars (device, 32 B LE each) against SRS points
 // [srs_off, srs_off + n); result XYZZ (Montgomery) written to d_out (device).
 int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, XYZZ* d_out);
+// the two halves of msm_xyzz, for callers that accumulate several scalar chunks into bucket sets of
+// the same window c before one final reduce (upload pipeline in capi.cu)
+int msm_pick_window(const myzkp_ctx* ctx, size_t n);
+int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets);
+int msm_add_buckets(myzkp_ctx* ctx, XYZZ* a, const XYZZ* b, int c);
+int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out);
 // XYZZ (device) -> canonical affine 64 B (device)
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
 int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);

@@ -290,16 +290,43 @@ static int tree_sum(myzkp_ctx* ctx, XYZZ* a, XYZZ* b, uint64_t count, XYZZ* d_ou
   }
 }
 
+int msm_pick_window(const myzkp_ctx* ctx, size_t n) { return pick_window(ctx, n); }
+
+// a[k] += b[k] over a whole bucket set (dense: every lane has an addition to do)
+__global__ void __launch_bounds__(128) msm_bucket_add(XYZZ* __restrict__ a, const XYZZ* __restrict__ b, uint32_t nb) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  XYZZ x = load_xyzz(a + k);
+  XYZZ y = load_xyzz(b + k);
+  xyzz_add(x, y);
+  store_xyzz(a + k, x);
+}
+
+int msm_add_buckets(myzkp_ctx* ctx, XYZZ* a, const XYZZ* b, int c) {
+  const uint32_t nb = 1u << (c - 1);
+  msm_bucket_add<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(a, b, nb);
+  MZ_LAUNCH_CHECK(ctx);
+  return MYZKP_OK;
+}
+
 int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, XYZZ* d_out) {
   if (n == 0) {
     xyzz_set_inf<<<1, 1, 0, ctx->stream>>>(d_out);
     MZ_LAUNCH_CHECK(ctx);
     return MYZKP_OK;
   }
+  const int c = pick_window(ctx, n);
+  MZ_CUDA_TRY(ctx, ctx->buckets.ensure(((size_t)1 << (c - 1)) * sizeof(XYZZ)));
+  MZ_TRY(msm_fill_buckets(ctx, d_scalars, n, srs_off, c, ctx->buckets.as<XYZZ>()));
+  return msm_reduce_buckets(ctx, c, ctx->buckets.as<XYZZ>(), d_out);
+}
+
+// steps 1-4: recode, sort, accumulate, merge -> `buckets` (2^(c-1) XYZZ, overwritten) holds the
+// bucket sums of sum_i scalars[i] * SRS[srs_off + i] for window c
+int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets) {
   if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
   if (srs_off + n > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
-
-  const int c = pick_window(ctx, n);
+  if (c < 1 || c > 24 || !((ctx->windows >> c) & 1)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
   const int W = (255 + c - 1) / c;
   const uint32_t nb = 1u << (c - 1);
   const uint64_t M = (uint64_t)W * n;
@@ -309,7 +336,6 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   MZ_CUDA_TRY(ctx, ctx->keys_b.ensure(M * 4));
   MZ_CUDA_TRY(ctx, ctx->vals_a.ensure(M * 4));
   MZ_CUDA_TRY(ctx, ctx->vals_b.ensure(M * 4));
-  MZ_CUDA_TRY(ctx, ctx->buckets.ensure((size_t)nb * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
   int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 512);
 
@@ -360,18 +386,17 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
-  MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(2);
   // batched-affine rounds pay off when runs are long enough to pair up (avg run >= 4)
   int baa = ctx->baa_rounds;
   if (baa < 0) baa = 0;  // automatic: off until measured faster on the target
   if (baa > 0 && L >= 4) {
-    MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
+    MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, buckets, ctx->heads.as<XYZZ>(),
                           ctx->head_keys.as<uint32_t>(), T));
   } else {
     msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-        keys_s, vals_s, M, L, nb, ctx->table, ctx->buckets.as<XYZZ>(), ctx->heads.as<XYZZ>(),
-        ctx->head_keys.as<uint32_t>(), T);
+        keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
     MZ_LAUNCH_CHECK(ctx);
   }
 
@@ -392,8 +417,7 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
       XYZZ* nh = reinterpret_cast<XYZZ*>(base);
       uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
       if (Tc > kMergeFan) MZ_CUDA_TRY(ctx, cudaMemsetAsync(nk, 0xff, T2 * sizeof(uint32_t), ctx->stream));
-      msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), cur_heads, cur_keys,
-                                                                             Tc, nb, nh, nk);
+      msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(buckets, cur_heads, cur_keys, Tc, nb, nh, nk);
       MZ_LAUNCH_CHECK(ctx);
       if (Tc <= kMergeFan) break;  // every head was inside the first cut: nothing was forwarded
       cur_heads = nh;
@@ -403,26 +427,35 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
     }
   }
   MZ_PHASE(4);
-  // 5. bucket reduce + tree sum
-  // chunk length: about one wave of (3 blocks x 128 threads) per SM
-  uint32_t Lb = 8;
-  while (Lb < 64 && (uint64_t)nb / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
-  uint32_t nchunks = (nb + Lb - 1) / Lb;
-  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
-  MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
-  msm_bucket_reduce<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->buckets.as<XYZZ>(), nb, Lb,
-                                                                    ctx->red_a.as<XYZZ>());
-  MZ_LAUNCH_CHECK(ctx);
-  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out));
-  MZ_PHASE(5);
 #undef MZ_PHASE
-  ctx->phase_valid[slot] = timing;
   ctx->msm_info[slot][0] = (uint64_t)c;
   ctx->msm_info[slot][1] = (uint64_t)W;
   ctx->msm_info[slot][2] = M;
   ctx->msm_info[slot][3] = L;
   ctx->msm_info[slot][4] = T;
   ctx->msm_info[slot][5] = nb;
+  ctx->phase_valid[slot] = false;  // set by msm_reduce_buckets once event 5 is recorded
+  ctx->phase_pending = timing;
+  return MYZKP_OK;
+}
+
+// step 5: sum_k (k+1) * buckets[k] -> *d_out (XYZZ)
+int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out) {
+  const uint32_t nb = 1u << (c - 1);
+  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
+  const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
+  // chunk length: about one wave of (3 blocks x 128 threads) per SM
+  uint32_t Lb = 8;
+  while (Lb < 64 && (uint64_t)nb / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
+  uint32_t nchunks = (nb + Lb - 1) / Lb;
+  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
+  msm_bucket_reduce<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(buckets, nb, Lb, ctx->red_a.as<XYZZ>());
+  MZ_LAUNCH_CHECK(ctx);
+  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out));
+  if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][5], ctx->stream));
+  ctx->phase_valid[slot] = timing;
+  ctx->phase_pending = false;
   ctx->msm_count++;
   return MYZKP_OK;
 }

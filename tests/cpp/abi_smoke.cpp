@@ -1,0 +1,49 @@
+// C++ host using the header-only mirror of the reference surface (include/myzkp_b200.hpp) over the C ABI.
+// Reproduces the reference's test_kzg polynomial (kzg.rs:152-175: (x+1)(x+2)(x+3), z = 5) with the fixed
+// alpha = 123456789 and compares with the anchor values pinned in SURVEY.md appendix B / tests/test_oracle_kats.py.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "myzkp_b200.hpp"
+
+using namespace myzkp_b200;
+
+static Scalar scalar_u64(uint64_t v) {
+  Scalar s{};
+  memcpy(s.data(), &v, 8);
+  return s;
+}
+static std::string hex_be(const uint8_t* le32) {
+  char buf[65];
+  for (int i = 0; i < 32; i++) snprintf(buf + 2 * i, 3, "%02x", le32[31 - i]);
+  return std::string(buf);
+}
+
+int main() {
+  try {
+    PublicKeyKZG pk(0);
+    setup_kzg(pk, 3, scalar_u64(123456789));
+    if (pk.size() != 4) { printf("FAIL srs size\n"); return 1; }
+    Polynomial f;
+    for (uint64_t c : {6, 11, 6, 1}) f.coef.push_back(scalar_u64(c));
+    CommitmentKZG c = commit_kzg(f, pk);
+    ProofKZG pr = open_kzg(f, scalar_u64(5), pk);
+    // printed big-endian so the Python side can compare with the decimal anchors
+    printf("C.x %s\nC.y %s\ny %s\nW.x %s\nW.y %s\n", hex_be(c.xy.data()).c_str(), hex_be(c.xy.data() + 32).c_str(),
+           hex_be(pr.y.data()).c_str(), hex_be(pr.w.xy.data()).c_str(), hex_be(pr.w.xy.data() + 32).c_str());
+    // empty polynomial commits to infinity; a too-long polynomial throws where the reference panics
+    Polynomial empty;
+    if (!commit_kzg(empty, pk).is_point_at_infinity()) { printf("FAIL empty\n"); return 1; }
+    Polynomial too_long = f;
+    too_long.coef.push_back(scalar_u64(1));
+    bool threw = false;
+    try { commit_kzg(too_long, pk); } catch (const std::runtime_error&) { threw = true; }
+    if (!threw) { printf("FAIL no error for deg > max_d\n"); return 1; }
+    printf("OK\n");
+  } catch (const std::exception& e) {
+    printf("FAIL %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -378,3 +378,24 @@ def test_generic_msm_with_caller_points(ctx):
     coefs = [rnd.randrange(R) for _ in range(64)]
     assert ctx.srs_len == 64
     assert ctx.g1_msm(coefs) == o.expected_commit(coefs, alpha) == ctx.commit(coefs)
+
+
+def test_cpp_host_through_header_mirror():
+    """tests/cpp/abi_smoke.cpp: a C++ host over include/myzkp_b200.hpp reproduces the test_kzg anchor."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "abi_smoke")
+    src = os.path.join(root, "tests", "cpp", "abi_smoke.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), "-o", exe, src,
+                               "-L", os.path.join(root, "myzkp_b200"), "-lmyzkp_b200",
+                               "-Wl,-rpath," + os.path.join(root, "myzkp_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    vals = dict(line.split() for line in out.strip().splitlines() if " " in line)
+    assert out.strip().endswith("OK"), out
+    assert int(vals["C.x"], 16) == 8096424998935924997123460782489249937183001369792870392058374165119638207724
+    assert int(vals["C.y"], 16) == 14698683656276342473960081670169131092130433153277961881223581660609015832377
+    assert int(vals["y"], 16) == 336
+    assert int(vals["W.x"], 16) == 15737316170989375530370354340609809222984715696988518295913516551941326522818
+    assert int(vals["W.y"], 16) == 13254863773102499080085687663253363332659578358445016579269372167128026496803

@@ -9,6 +9,8 @@
 //                     digit counters + __match_any_sync ranking), then a coalesced
 //                     copy-out of each digit run to its global base
 // Per pass and entry: 4 B (histogram read) + 8 B read + 8 B write = 20 B of HBM traffic.
+// The scatter kernel is persistent (2 blocks per SM) and prefetches the next tile into
+// registers; peer masks come from ballots (MATCH.ANY was the bottleneck of an earlier version).
 // Stability is not needed by the MSM (bucket sums commute) but keeps the sort a plain
 // LSD radix sort whose result is independent of scheduling.
 #include "ctx.cuh"
@@ -105,6 +107,21 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(uint32_t* __restrict_
 // ---------------------------------------------------------------------------
 // pass kernels
 // ---------------------------------------------------------------------------
+// Lanes of the warp holding the same 8-bit digit (and the same validity): nine ballots and a
+// few logic ops.  MATCH.ANY computes the same mask in one instruction, but its throughput
+// (~1 per 64 cycles per SM, measured through the scatter kernel) made it the bottleneck.
+__device__ __forceinline__ uint32_t warp_match_digit(uint32_t d, bool valid) {
+  uint32_t peers = __ballot_sync(0xffffffffu, valid);
+  if (!valid) peers = ~peers;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t ball = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? ball : ~ball;
+  }
+  return peers;
+}
+
 __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* __restrict__ keys, uint64_t n, int shift,
                                                                uint32_t* __restrict__ hist, uint32_t ntiles) {
   __shared__ uint32_t h[kRadix];
@@ -134,7 +151,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
   hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads, 4)
+// Persistent: each block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile's keys,
+// values and digit bases are fetched into registers before the current tile is ranked, so the
+// DRAM latency is covered by the ranking work rather than by occupancy.
+__global__ void __launch_bounds__(kSortThreads, 2)
     sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
                       const uint32_t* __restrict__ hist_scanned, uint32_t ntiles, uint32_t* __restrict__ keys_out,
                       uint32_t* __restrict__ vals_out) {
@@ -145,93 +165,106 @@ __global__ void __launch_bounds__(kSortThreads, 4)
   __shared__ uint32_t gbase[kRadix];            // global base of each digit run of this tile
   __shared__ uint32_t ws[33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint64_t tile_base = (uint64_t)blockIdx.x * kSortTile;
-  const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)kSortTile ? (n - tile_base) : kSortTile);
-#pragma unroll
-  for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
-  gbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * ntiles + blockIdx.x];
-  __syncthreads();
-
   // warp-blocked arrangement: warp w owns tile entries [w*512, (w+1)*512) in index order
-  uint32_t k[kSortItems], rank[kSortItems];
   const uint32_t wbase = (uint32_t)w * (32 * kSortItems);
+
+  uint32_t k[kSortItems], v[kSortItems], kn[kSortItems], vn[kSortItems], rank[kSortItems];
+  uint32_t gb = 0, gbn = 0;
+  auto fetch = [&](uint32_t tile, uint32_t* kk, uint32_t* vv, uint32_t& g) {
+    const uint64_t tb = (uint64_t)tile * kSortTile;
+    const uint32_t tn = (uint32_t)((n - tb) < (uint64_t)kSortTile ? (n - tb) : kSortTile);
 #pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = wbase + i * 32 + lane;
-    k[i] = p < tile_n ? keys_in[tile_base + p] : 0xffffffffu;
-  }
-  // all 16 matches first (they only depend on the keys, so they pipeline), then the
-  // sequential per-warp counter updates
-#pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = wbase + i * 32 + lane;
-    uint32_t d = p < tile_n ? ((k[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // 256 = padding, never a digit
-    rank[i] = __match_any_sync(0xffffffffu, d);  // peers: lanes of this warp with the same digit in this round
-  }
-#pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = wbase + i * 32 + lane;
-    bool ok = p < tile_n;
-    uint32_t d = (k[i] >> shift) & (kRadix - 1);
-    uint32_t peers = rank[i];
-    uint32_t before = __popc(peers & ((1u << lane) - 1u));
-    uint32_t prev = 0;
-    if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter
-      prev = cnt[w][d];
-      cnt[w][d] = prev + __popc(peers);
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = wbase + i * 32 + lane;
+      kk[i] = p < tn ? keys_in[tb + p] : 0xffffffffu;
     }
-    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    rank[i] = prev + before;
-    __syncwarp();
-  }
-  // the values are only needed for the placement: fetch them while the digit scan runs
-  uint32_t v[kSortItems];
 #pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = wbase + i * 32 + lane;
-    v[i] = p < tile_n ? vals_in[tile_base + p] : 0u;
-  }
-  __syncthreads();
-  // digit totals -> exclusive scan over digits -> per-warp bases
-  {
-    uint32_t tot = 0;
-#pragma unroll
-    for (int i = 0; i < kSortWarps; i++) tot += cnt[i][threadIdx.x];
-    uint32_t total;
-    uint32_t ex = block_excl_scan(tot, ws, total);
-    digit_start[threadIdx.x] = ex;
-    uint32_t run = ex;
-#pragma unroll
-    for (int i = 0; i < kSortWarps; i++) {
-      uint32_t c = cnt[i][threadIdx.x];
-      cnt[i][threadIdx.x] = run;
-      run += c;
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = wbase + i * 32 + lane;
+      vv[i] = p < tn ? vals_in[tb + p] : 0u;
     }
-  }
-  __syncthreads();
-  // place into shared memory in digit order
+    g = hist_scanned[(size_t)threadIdx.x * ntiles + tile];
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile, kn, vn, gbn);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const uint64_t tile_base = (uint64_t)tile * kSortTile;
+    const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)kSortTile ? (n - tile_base) : kSortTile);
 #pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = wbase + i * 32 + lane;
-    if (p < tile_n) {
+    for (int i = 0; i < kSortItems; i++) { k[i] = kn[i]; v[i] = vn[i]; }
+    gb = gbn;
+    if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x, kn, vn, gbn);  // in flight during the ranking below
+#pragma unroll
+    for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
+    gbase[threadIdx.x] = gb;
+    __syncthreads();
+    // all 16 matches first (they only depend on the keys, so they pipeline), then the
+    // sequential per-warp counter updates
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = wbase + i * 32 + lane;
       uint32_t d = (k[i] >> shift) & (kRadix - 1);
-      uint32_t pos = cnt[w][d] + rank[i];
-      s_keys[pos] = k[i];
-      s_vals[pos] = v[i];
+      rank[i] = warp_match_digit(d, p < tile_n);  // peers: lanes of this warp with the same digit in this round
     }
-  }
-  __syncthreads();
-  // coalesced copy-out of the digit runs
 #pragma unroll
-  for (int i = 0; i < kSortItems; i++) {
-    uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
-    if (p < tile_n) {
-      uint32_t key = s_keys[p];
-      uint32_t d = (key >> shift) & (kRadix - 1);
-      uint64_t g = (uint64_t)gbase[d] + (p - digit_start[d]);
-      keys_out[g] = key;
-      vals_out[g] = s_vals[p];
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = wbase + i * 32 + lane;
+      bool ok = p < tile_n;
+      uint32_t d = (k[i] >> shift) & (kRadix - 1);
+      uint32_t peers = rank[i];
+      uint32_t before = __popc(peers & ((1u << lane) - 1u));
+      uint32_t prev = 0;
+      if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter
+        prev = cnt[w][d];
+        cnt[w][d] = prev + __popc(peers);
+      }
+      prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+      rank[i] = prev + before;
+      __syncwarp();
     }
+    __syncthreads();
+    // digit totals -> exclusive scan over digits -> per-warp bases
+    {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int i = 0; i < kSortWarps; i++) tot += cnt[i][threadIdx.x];
+      uint32_t total;
+      uint32_t ex = block_excl_scan(tot, ws, total);
+      digit_start[threadIdx.x] = ex;
+      uint32_t run = ex;
+#pragma unroll
+      for (int i = 0; i < kSortWarps; i++) {
+        uint32_t c = cnt[i][threadIdx.x];
+        cnt[i][threadIdx.x] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    // place into shared memory in digit order
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = wbase + i * 32 + lane;
+      if (p < tile_n) {
+        uint32_t d = (k[i] >> shift) & (kRadix - 1);
+        uint32_t pos = cnt[w][d] + rank[i];
+        s_keys[pos] = k[i];
+        s_vals[pos] = v[i];
+      }
+    }
+    __syncthreads();
+    // coalesced copy-out of the digit runs
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
+      if (p < tile_n) {
+        uint32_t key = s_keys[p];
+        uint32_t d = (key >> shift) & (kRadix - 1);
+        uint64_t g = (uint64_t)gbase[d] + (p - digit_start[d]);
+        keys_out[g] = key;
+        vals_out[g] = s_vals[p];
+      }
+    }
+    __syncthreads();  // shared arrays are reused by the next tile
   }
 }
 
@@ -262,7 +295,8 @@ int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_
     MZ_LAUNCH_CHECK(ctx);
     scan_apply<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
     MZ_LAUNCH_CHECK(ctx);
-    sort_tile_scatter<<<ntiles, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo);
+    const uint32_t sblocks = ntiles < (uint32_t)ctx->sm_count * 2 ? ntiles : (uint32_t)ctx->sm_count * 2;
+    sort_tile_scatter<<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo);
     MZ_LAUNCH_CHECK(ctx);
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;

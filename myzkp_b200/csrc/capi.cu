@@ -74,6 +74,47 @@ int end_call_check_flag(myzkp_ctx* ctx) {
   return MYZKP_OK;
 }
 
+constexpr int kMaxChildren = 8;
+
+void free_ctx_scratch(myzkp_ctx* ctx) {
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
+                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
+  for (DevBuf* b : bufs) b->release();
+}
+
+// child i of ctx, (re)pointed at the parent's current SRS table
+int get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out) {
+  while ((int)ctx->children.size() <= i) {
+    myzkp_ctx* c = new myzkp_ctx();
+    c->is_child = true;
+    c->device = ctx->device;
+    c->sm_count = ctx->sm_count;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess) {
+      delete c;
+      return fail(ctx, MYZKP_ERR_CUDA, "cannot create a child stream");
+    }
+    c->own_stream = true;
+    ctx->children.push_back(c);
+  }
+  myzkp_ctx* c = ctx->children[i];
+  c->table = ctx->table;
+  c->srs_n = ctx->srs_n;
+  c->table_rows = ctx->table_rows;
+  c->windows = ctx->windows;
+  memcpy(c->row_bits, ctx->row_bits, sizeof c->row_bits);
+  memcpy(c->row_of_bit, ctx->row_of_bit, sizeof c->row_of_bit);
+  c->d_row_of_bit = ctx->d_row_of_bit;
+  c->d_row_bits = ctx->d_row_bits;
+  c->window_bits = ctx->window_bits;
+  c->segment_len = ctx->segment_len;
+  c->baa_rounds = ctx->baa_rounds;
+  *out = c;
+  return MYZKP_OK;
+}
+
 // MSM of n scalars that arrive in K upload chunks (events ctx->copy_ev[k]).  With u_le != NULL the
 // scalars are the quotient of the uploaded polynomial by (x - u): chunks are then consumed top first,
 // the scan carry stays on the device, and y is left at kSmallY.
@@ -149,11 +190,16 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   if (ctx->gcomb) cudaFree(ctx->gcomb);
   if (ctx->d_row_of_bit) cudaFree(ctx->d_row_of_bit);
   if (ctx->d_row_bits) cudaFree(ctx->d_row_bits);
-  DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
-                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans, &ctx->red_a, &ctx->red_b,
-                    &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
-  for (DevBuf* b : bufs) b->release();
+  for (myzkp_ctx* c : ctx->children) {
+    cudaStreamSynchronize(c->stream);
+    free_ctx_scratch(c);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+  }
+  ctx->children.clear();
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  free_ctx_scratch(ctx);
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
     for (int i = 0; i < 6; i++)
       if (ctx->phase_ev[s][i]) cudaEventDestroy(ctx->phase_ev[s][i]);
@@ -382,16 +428,50 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
   uint8_t* d_pts = reinterpret_cast<uint8_t*>(res + (m + 1));
   int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag);
   MZ_TRY(fr_check_canonical(ctx, base, n_pow2, flag));
-  uint32_t* cur = base;
-  size_t len = n_pow2;
-  for (int lvl = 0; lvl <= m; lvl++) {
-    MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
-    if (lvl < m) {
+  // all folds first (each level depends on the previous one; they are cheap element-wise kernels) ...
+  {
+    uint32_t* cur = base;
+    size_t len = n_pow2;
+    for (int lvl = 0; lvl < m; lvl++) {
       uint32_t* nxt = cur + len * 8;
       MZ_TRY(fr_fold(ctx, cur, len / 2, d_rhos + 8 * lvl, nxt));
       cur = nxt;
       len /= 2;
     }
+  }
+  // ... then one MSM per level.  Small levels are latency-bound, so they run concurrently on child
+  // contexts (own stream and scratch, same SRS table) while the large levels run on this stream.
+  const size_t small_below = (size_t)1 << 19;
+  if (!ctx->fork_ev) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  int used_children = 0, next_child = 0;
+  {
+    uint32_t* cur = base;
+    size_t len = n_pow2;
+    for (int lvl = 0; lvl <= m; lvl++) {
+      if (len >= small_below) {
+        MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
+      } else {
+        myzkp_ctx* ch = nullptr;
+        MZ_TRY(get_child(ctx, next_child, &ch));
+        if (next_child >= used_children) {  // first use in this call: wait for the folds
+          MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, ctx->fork_ev, 0));
+          used_children = next_child + 1;
+        }
+        int rc = msm_xyzz(ch, cur, len, 0, res + lvl);
+        if (rc != MYZKP_OK) return fail(ctx, rc, ch->err.c_str());
+        ctx->launches += ch->launches;
+        ch->launches = 0;
+        next_child = (next_child + 1) % kMaxChildren;
+      }
+      cur += len * 8;
+      len /= 2;
+    }
+  }
+  for (int i = 0; i < used_children; i++) {
+    myzkp_ctx* ch = ctx->children[i];
+    MZ_CUDA_TRY(ctx, cudaEventRecord(ch->join_ev, ch->stream));
+    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0));
   }
   MZ_TRY(xyzz_to_bytes(ctx, res, (size_t)(m + 1), d_pts));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pts, (size_t)(m + 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));

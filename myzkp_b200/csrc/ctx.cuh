@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/myzkp_b200.h"
 #include "g1.cuh"
@@ -48,6 +49,12 @@ struct DevBuf {
 }  // namespace mz
 
 struct myzkp_ctx {
+  // Child contexts: own stream and scratch, SRS table shared with (and owned by) the parent.
+  // Used to run many small, latency-bound MSMs concurrently (Gemini's low levels).
+  std::vector<myzkp_ctx*> children;
+  bool is_child = false;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;

@@ -58,8 +58,9 @@ int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds);
 
 /* Host-buffer commit/open upload a large polynomial in chunks on a copy stream while
  * earlier chunks are already being processed (each chunk is an MSM against its own SRS
- * range; the partial points are summed).  0 = automatic (1 below 2^23 coefficients,
- * 2 at 2^23, 4 from 2^24), 1..8 forces a chunk count. */
+ * range and the same window; the bucket sets are added and reduced once).  Chunk sizes grow
+ * 4x so only the small first upload is exposed.  0 = automatic (1 below 2^22 coefficients,
+ * 2 from 2^22, 3 from 2^24), 1..8 forces a chunk count. */
 int myzkp_ctx_set_upload_chunks(myzkp_ctx* ctx, int chunks);
 
 /* Per-phase CUDA-event timing of the MSM (events on the ctx stream, kept for the

@@ -37,9 +37,25 @@ int begin_call(myzkp_ctx* ctx) {
 // Upload pipeline for the host-buffer entry points: how many chunks to split n into
 int upload_chunks(const myzkp_ctx* ctx, size_t n) {
   if (ctx->upload_chunks > 0) return (size_t)ctx->upload_chunks <= (n ? n : 1) ? ctx->upload_chunks : 1;
-  if (n >= ((size_t)1 << 24)) return 4;
-  if (n >= ((size_t)1 << 23)) return 2;
+  if (n >= ((size_t)1 << 24)) return 3;
+  if (n >= ((size_t)1 << 22)) return 2;
   return 1;
+}
+// Chunk `pos` (in processing order) of n coefficients cut into K chunks whose sizes grow 4x: the
+// MSM of a chunk takes about four times as long as its upload, so a chunk four times larger can be
+// uploaded meanwhile and only the small first upload is exposed.  Descending: the first chunk
+// processed is the top of the polynomial (the quotient scan runs downwards).
+void chunk_range(size_t n, int K, int pos, bool descending, size_t* lo, size_t* hi) {
+  const unsigned __int128 total = (((unsigned __int128)1 << (2 * K)) - 1);
+  auto cum = [&](int p) { return (size_t)(((unsigned __int128)n * ((((unsigned __int128)1) << (2 * p)) - 1)) / total); };
+  size_t a = cum(pos), b = pos + 1 == K ? n : cum(pos + 1);
+  if (descending) {
+    *lo = n - b;
+    *hi = n - a;
+  } else {
+    *lo = a;
+    *hi = b;
+  }
 }
 int ensure_copy_stream(myzkp_ctx* ctx) {
   if (ctx->copy_stream) return MYZKP_OK;
@@ -54,13 +70,12 @@ int enqueue_chunk_uploads(myzkp_ctx* ctx, const uint8_t* host, uint8_t* dev, siz
   // the copy stream must not overwrite the staging buffer while earlier work on `stream` still reads it
   MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done_ev, ctx->stream));
   MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done_ev, 0));
-  const size_t per = (n + K - 1) / K;
-  for (int i = 0; i < K; i++) {
-    int k = descending ? K - 1 - i : i;
-    size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
-    if (lo >= hi) { MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream)); continue; }
-    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(dev + lo * 32, host + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+  for (int pos = 0; pos < K; pos++) {
+    size_t lo, hi;
+    chunk_range(n, K, pos, descending, &lo, &hi);
+    if (lo < hi)
+      MZ_CUDA_TRY(ctx, cudaMemcpyAsync(dev + lo * 32, host + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[pos], ctx->copy_stream));
   }
   return MYZKP_OK;
 }
@@ -130,13 +145,12 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
   MZ_CUDA_TRY(ctx, ctx->buckets.ensure(2 * nb * sizeof(XYZZ)));
   XYZZ* b0 = ctx->buckets.as<XYZZ>();
   XYZZ* b1 = b0 + nb;
-  const size_t per = (n + K - 1) / K;
   bool first = true;
-  for (int i = 0; i < K; i++) {
-    const int k = descending ? K - 1 - i : i;
-    size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+  for (int pos = 0; pos < K; pos++) {
+    size_t lo, hi;
+    chunk_range(n, K, pos, descending, &lo, &hi);
+    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[pos], 0));
     if (lo >= hi) continue;
-    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
     const uint32_t* sc = d_coefs + lo * 8;
     size_t len = hi - lo;
     if (u_le) {

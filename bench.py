@@ -212,8 +212,7 @@ def main():
     def step_e2e():
         if world == 1:
             return mz.commit_kzg(mz.Polynomial(pinned_scal), pk)  # public API, host buffers
-        d_scal[: n_local * 4].copy_(h2d_tensor, non_blocking=True)
-        prover.commit(d_scal.data_ptr(), out)
+        prover.commit_host(pinned_scal, out)  # pipelined upload of this rank's slice + MSM + NCCL exchange
         return out.cpu()
 
     # ---- correctness before timing ---------------------------------------------------

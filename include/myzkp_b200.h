@@ -138,6 +138,10 @@ int myzkp_kzg_open_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint
  * over NCCL and summed with myzkp_g1_sum_partials_dev. */
 int myzkp_g1_msm_partial_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n, size_t srs_off,
                              void* d_out_xyzz128);
+/* Same with the scalars in host memory (pinned for full speed): uploads them through the chunked
+ * pipeline, asynchronously on the ctx stream, and leaves the XYZZ partial on the device.  The host
+ * buffer must stay valid until the stream has been synchronised. */
+int myzkp_g1_msm_partial(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n, size_t srs_off, void* d_out_xyzz128);
 /* Sum k XYZZ partials (k*128 B, device) -> canonical affine 64 B (device). */
 int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64);
 /* Sharded open: per-rank pieces of the quotient scan over a contiguous

@@ -47,6 +47,7 @@ SIGNATURES = {
     "myzkp_kzg_commit_dev": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_kzg_open_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_g1_msm_partial_dev": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "myzkp_g1_msm_partial": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "myzkp_g1_sum_partials_dev": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_fr_range_eval_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_fr_range_quotient_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),

@@ -251,6 +251,12 @@ def _dev_methods():
         self._ck(self._lib.myzkp_g1_msm_partial_dev(self.h, ctypes.c_void_p(d_scalars), n, srs_off,
                                                     ctypes.c_void_p(d_out_xyzz128)))
 
+    def msm_partial_host(self, scalars: np.ndarray, srs_off: int, d_out_xyzz128: int):
+        """Host (ideally pinned) scalars -> XYZZ partial on the device; asynchronous on the ctx stream."""
+        a = scalars_to_bytes(scalars)
+        self._keepalive = a  # the upload is asynchronous
+        self._ck(self._lib.myzkp_g1_msm_partial(self.h, _ptr(a), a.shape[0], srs_off, ctypes.c_void_p(d_out_xyzz128)))
+
     def sum_partials_dev(self, d_partials: int, k: int, d_out64: int):
         self._ck(self._lib.myzkp_g1_sum_partials_dev(self.h, ctypes.c_void_p(d_partials), k, ctypes.c_void_p(d_out64)))
 
@@ -265,7 +271,7 @@ def _dev_methods():
         self._ck(self._lib.myzkp_fr_range_quotient_dev(self.h, ctypes.c_void_p(d_coefs), n, _ptr(ub), _ptr(cb),
                                                        ctypes.c_void_p(d_q), ctypes.c_void_p(d_c0)))
 
-    for f in (commit_dev, open_dev, msm_partial_dev, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev):
+    for f in (commit_dev, open_dev, msm_partial_dev, msm_partial_host, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev):
         setattr(Context, f.__name__, f)
 
 

@@ -134,7 +134,7 @@ int get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out) {
 // scalars are the quotient of the uploaded polynomial by (x - u): chunks are then consumed top first,
 // the scan carry stays on the device, and y is left at kSmallY.
 int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descending, const uint8_t* u_le,
-                uint32_t* d_quot, XYZZ* d_res) {
+                uint32_t* d_quot, XYZZ* d_res, size_t srs_off = 0) {
   uint8_t* s = ctx->small.as<uint8_t>();
   uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallY);  // carry chain, ends as y
   uint32_t* c0_prev = reinterpret_cast<uint32_t*>(s + kSmallY + 32);
@@ -163,7 +163,7 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
       if (top) len -= 1;
     }
     if (len == 0) continue;
-    MZ_TRY(msm_fill_buckets(ctx, sc, len, lo, c, first ? b0 : b1));
+    MZ_TRY(msm_fill_buckets(ctx, sc, len, srs_off + lo, c, first ? b0 : b1));
     if (!first) MZ_TRY(msm_add_buckets(ctx, b0, b1, c));
     first = false;
   }
@@ -303,6 +303,22 @@ int myzkp_g1_msm_partial_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n, si
   if (!ctx || (!d_scalars && n) || !d_out_xyzz128) return MYZKP_ERR_INVALID_ARG;
   MZ_TRY(begin_call(ctx));
   return msm_xyzz(ctx, static_cast<const uint32_t*>(d_scalars), n, srs_off, static_cast<XYZZ*>(d_out_xyzz128));
+}
+
+int myzkp_g1_msm_partial(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n, size_t srs_off, void* d_out_xyzz128) {
+  if (!ctx || (!scalars_le && n) || !d_out_xyzz128) return MYZKP_ERR_INVALID_ARG;
+  if (srs_off + n > ctx->srs_n) return fail(ctx, n && !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG,
+                                            "scalar range longer than the SRS");
+  MZ_TRY(begin_call(ctx));
+  const int K = upload_chunks(ctx, n);
+  if (n) MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+  if (K == 1) {
+    if (n) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_xyzz(ctx, ctx->scalars.as<uint32_t>(), n, srs_off, static_cast<XYZZ*>(d_out_xyzz128));
+  }
+  MZ_TRY(enqueue_chunk_uploads(ctx, scalars_le, ctx->scalars.as<uint8_t>(), n, K, false));
+  return chunked_msm(ctx, ctx->scalars.as<uint32_t>(), n, K, false, nullptr, nullptr, static_cast<XYZZ*>(d_out_xyzz128),
+                     srs_off);
 }
 
 int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64) {

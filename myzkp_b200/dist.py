@@ -60,6 +60,10 @@ class DeviceOps:
         self.ctx.msm_partial_dev(d_scalars, n, 0, self.partial.data_ptr())
         return self.partial
 
+    def msm_partial_host(self, host_scalars, n: int) -> torch.Tensor:
+        self.ctx.msm_partial_host(host_scalars[:n], 0, self.partial.data_ptr())
+        return self.partial
+
     def sum_partials(self, gathered: torch.Tensor, k: int, out64: torch.Tensor) -> None:
         self.ctx.sum_partials_dev(gathered.data_ptr(), k, out64.data_ptr())
 
@@ -98,6 +102,12 @@ class ShardedKZG:
         """d_scalars_local: this rank's coefficient slice [lo, hi) (device address)."""
         n = self.n_local if n_local is None else n_local
         partial = self.ops.msm_partial(d_scalars_local, n)
+        gathered = self._all_gather(partial, "_gather128")
+        self.ops.sum_partials(gathered, self.world, out64)
+
+    def commit_host(self, host_scalars_local, out64: torch.Tensor) -> None:
+        """Same with this rank's coefficient slice in host (pinned) memory: upload pipelined with the MSM."""
+        partial = self.ops.msm_partial_host(host_scalars_local, self.n_local)
         gathered = self._all_gather(partial, "_gather128")
         self.ops.sum_partials(gathered, self.world, out64)
 

@@ -56,6 +56,8 @@ extern "C" {
                               d_out_y32: *mut c_void, d_out_w64: *mut c_void) -> c_int;
     pub fn myzkp_g1_msm_partial_dev(ctx: *mut myzkp_ctx, d_scalars: *const c_void, n: usize, srs_off: usize,
                                     d_out_xyzz128: *mut c_void) -> c_int;
+    pub fn myzkp_g1_msm_partial(ctx: *mut myzkp_ctx, scalars_le: *const u8, n: usize, srs_off: usize,
+                                d_out_xyzz128: *mut c_void) -> c_int;
     pub fn myzkp_g1_sum_partials_dev(ctx: *mut myzkp_ctx, d_partials: *const c_void, k: usize,
                                      d_out_c64: *mut c_void) -> c_int;
     pub fn myzkp_fr_range_eval_dev(ctx: *mut myzkp_ctx, d_coefs: *const c_void, n: usize, u_le: *const u8,

@@ -218,6 +218,15 @@ def test_sharded_commit_and_open_emulated_ranks(ctx):
     ranks[0][0].sum_partials_dev(partials.data_ptr(), world, out.data_ptr())
     ranks[0][0].sync()
     assert mz.context.point_from_bytes(out.cpu().numpy().tobytes()) == o.expected_commit(ints, alpha)
+    # the same partials from host scalars through the chunked upload pipeline
+    for r, (c, lo, hi) in enumerate(ranks):
+        c.set_upload_chunks(3)
+        c.msm_partial_host(coefs[lo:hi], 0, partials.data_ptr() + 128 * r)
+        c.sync()
+        c.set_upload_chunks(0)
+    ranks[2][0].sum_partials_dev(partials.data_ptr(), world, out.data_ptr())
+    ranks[2][0].sync()
+    assert mz.context.point_from_bytes(out.cpu().numpy().tobytes()) == o.expected_commit(ints, alpha)
     raw = pairs.cpu().numpy().tobytes()
     hs = [int.from_bytes(raw[64 * r : 64 * r + 32], "little") for r in range(world)]
     ms = [int.from_bytes(raw[64 * r + 32 : 64 * r + 64], "little") for r in range(world)]

@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-verify", action="store_true", help="skip the O(N) host check of the full-size commitment")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused peer-memory exchange kernel (default) or NCCL all_gather + sum")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--segment-len", type=int, default=0)
     args = ap.parse_args()
@@ -201,7 +203,13 @@ def main():
     d_scal = torch.empty(max(n_local, 1) * 4, dtype=torch.int64, device=dev)
     d_scal[: n_local * 4].copy_(torch.from_numpy(pinned_scal.view(np.int64).reshape(-1)))
     out = torch.zeros(64, dtype=torch.uint8, device=dev)
-    prover = ShardedKZG(DeviceOps(ctx, dev), rank, world, n_total)
+    ops = DeviceOps(ctx, dev)
+    exchange = "none (single GPU)"
+    if world > 1:
+        fused = args.exchange == "peer" and ops.attach_peers(rank, world)
+        exchange = ("one kernel over peer memory (NVLink stores + sum + affine, csrc/peer.cu)" if fused
+                    else "NCCL all_gather of 128 B partials + sum kernel")
+    prover = ShardedKZG(ops, rank, world, n_total)
     pk = mz.PublicKeyKZG(ctx)
 
     def step_resident():
@@ -212,6 +220,8 @@ def main():
     def step_e2e():
         if world == 1:
             return mz.commit_kzg(mz.Polynomial(pinned_scal), pk)  # public API, host buffers
+        if ops.fused:  # host slice in, commitment out: upload pipeline + MSM + peer-memory exchange, one C call
+            return ctx.commit_sharded(pinned_scal)
         prover.commit_host(pinned_scal, out)  # pipelined upload of this rank's slice + MSM + NCCL exchange
         return out.cpu()
 
@@ -274,9 +284,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / args.steps
     e2e_val = n_total / (e2e_ms * 1e-3)
-    e2e_point = res.as_tuple() if world == 1 else mz.context.point_from_bytes(res.numpy().tobytes())
+    if world == 1:
+        e2e_point = res.as_tuple()
+    else:
+        e2e_point = res if ops.fused else mz.context.point_from_bytes(res.numpy().tobytes())
     if e2e_point != got:
         raise SystemExit("bench.py: e2e path disagrees with the device-resident path")
+
+    # ---- N > 1: each rank's local MSM alone (no exchange), to split the step into compute and exchange ----
+    per_rank_local_ms = None
+    if world > 1:
+        for _ in range(2):
+            ops.msm_partial(d_scal.data_ptr(), n_local)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            ops.msm_partial(d_scal.data_ptr(), n_local)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        allv = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, mine)
+        per_rank_local_ms = [round(float(x), 4) for x in allv.cpu()]
 
     # ---- roofline of the dominant kernel (msm_accumulate) on this rank ------------------------
     peaks, imad = load_measured()
@@ -341,7 +370,7 @@ def main():
             "vs_baseline": None, "dtype": "u32x8 (254-bit modular integers, Montgomery)", "data": "synthetic",
             "config": {
                 "workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
-                "points_total": n_total, "points_per_gpu": n_local, "parallelism": f"range-sharded x{world}",
+                "points_total": n_total, "points_per_gpu": n_local, "parallelism": f"range-sharded x{world}", "exchange": exchange,
                 "l2": "inputs larger than L2 (scalars %d MiB + resident SRS table of 2^(b_j) multiples, >= %d MiB per GPU; no flush needed)"
                       % (n_local * 32 >> 20, n_local * 64 * 32 >> 20),
                 "window_bits": info.get("window_bits"), "srs_setup_s": t_srs,
@@ -354,6 +383,8 @@ def main():
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
             "phases_ms": phase_acc,
+            "per_rank_local_ms": per_rank_local_ms,
+            "exchange_ms": (ms_step - max(per_rank_local_ms)) if per_rank_local_ms else None,
             "cpu_baseline": cpu_baseline,
             "verified_vs_oracle": verified,
             "extra": extra,

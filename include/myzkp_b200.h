@@ -142,6 +142,32 @@ int myzkp_g1_msm_partial_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n, si
  * pipeline, asynchronously on the ctx stream, and leaves the XYZZ partial on the device.  The host
  * buffer must stay valid until the stream has been synchronised. */
 int myzkp_g1_msm_partial(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n, size_t srs_off, void* d_out_xyzz128);
+/* ---- exchange fused over peer memory (NVLink / NVSwitch), one process per GPU -----------------------
+ * Each rank owns a small exchange buffer that every peer maps (CUDA IPC).  The sharded entry points
+ * below end in ONE kernel that stores this rank's partial into all peers' buffers, waits for theirs
+ * and finishes (sum + affine, or scan-carry composition) in the same launch; no collective library
+ * call is on the path.  Set-up: every rank calls myzkp_peer_export, the ranks exchange the 64-byte
+ * handles out of band (e.g. torch.distributed.all_gather), every rank calls myzkp_peer_attach with
+ * all of them.  All ranks must then issue the same sequence of sharded calls.  A rank that waits
+ * longer than the timeout (default 10 s) reports MYZKP_ERR_CUDA from the next myzkp_ctx_sync. */
+#define MYZKP_PEER_HANDLE_BYTES 64
+int myzkp_peer_export(myzkp_ctx* ctx, uint8_t out_handle[MYZKP_PEER_HANDLE_BYTES]);
+int myzkp_peer_attach(myzkp_ctx* ctx, int rank, int world, const uint8_t* handles /* world * 64 B */);
+/* same for contexts living in ONE process (one host thread driving several GPUs or streams) */
+int myzkp_peer_attach_local(myzkp_ctx* ctx, int rank, int world, myzkp_ctx* const* ctxs);
+int myzkp_peer_detach(myzkp_ctx* ctx);
+int myzkp_peer_set_timeout_ms(myzkp_ctx* ctx, uint32_t ms);
+/* commit_kzg (kzg.rs:57-59) of a polynomial range-sharded over the attached ranks: this rank holds
+ * SRS points [lo, lo + n_local) and the matching coefficient slice; every rank ends with the same
+ * 64-byte commitment.  _dev: device pointers, asynchronous on the ctx stream. */
+int myzkp_kzg_commit_sharded_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n_local, void* d_out_c64);
+int myzkp_kzg_commit_sharded(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n_local, uint8_t out_c[64]);
+/* the exchange + sum + affine kernel on its own: this rank's XYZZ partial (device) -> the sum over ranks */
+int myzkp_g1_exchange_sum_dev(myzkp_ctx* ctx, const void* d_partial_xyzz128, void* d_out_c64);
+/* open_kzg (kzg.rs:61-72) over the same sharding: range evaluation, exchange + carry composition,
+ * local quotient scan, local MSM, exchange + sum.  Every rank ends with (y, W). */
+int myzkp_kzg_open_sharded_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n_local, const uint8_t u_le[32],
+                               void* d_out_y32, void* d_out_w64);
 /* Sum k XYZZ partials (k*128 B, device) -> canonical affine 64 B (device). */
 int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64);
 /* Sharded open: per-rank pieces of the quotient scan over a contiguous

@@ -4,6 +4,7 @@ setup_kzg / commit_kzg / open_kzg / commit_gemini surface.
 The work is done by libmyzkp_b200.so (hand-written CUDA for sm_100a, C ABI in
 include/myzkp_b200.h).  There is no CPU fallback.
 """
+from ._lib import MyzkpError  # noqa: F401
 from .context import Context, R_MOD, P_MOD  # noqa: F401
 from .kzg import (  # noqa: F401
     BN128, BatchProofKZG, CommitmentKZG, G1Point, Polynomial, ProofDegreeBound, ProofKZG, PublicKeyKZG,

@@ -48,6 +48,15 @@ SIGNATURES = {
     "myzkp_kzg_open_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_g1_msm_partial_dev": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "myzkp_g1_msm_partial": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "myzkp_peer_export": (_i, [_vp, _vp]),
+    "myzkp_peer_attach": (_i, [_vp, _i, _i, _vp]),
+    "myzkp_peer_attach_local": (_i, [_vp, _i, _i, _vp]),
+    "myzkp_peer_detach": (_i, [_vp]),
+    "myzkp_peer_set_timeout_ms": (_i, [_vp, ctypes.c_uint32]),
+    "myzkp_kzg_commit_sharded_dev": (_i, [_vp, _vp, _sz, _vp]),
+    "myzkp_g1_exchange_sum_dev": (_i, [_vp, _vp, _vp]),
+    "myzkp_kzg_commit_sharded": (_i, [_vp, _vp, _sz, _vp]),
+    "myzkp_kzg_open_sharded_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_g1_sum_partials_dev": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_fr_range_eval_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_fr_range_quotient_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),

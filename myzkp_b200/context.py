@@ -271,7 +271,52 @@ def _dev_methods():
         self._ck(self._lib.myzkp_fr_range_quotient_dev(self.h, ctypes.c_void_p(d_coefs), n, _ptr(ub), _ptr(cb),
                                                        ctypes.c_void_p(d_q), ctypes.c_void_p(d_c0)))
 
-    for f in (commit_dev, open_dev, msm_partial_dev, msm_partial_host, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev):
+    # ---- exchange fused over peer memory (csrc/peer.cu) ----
+    def peer_export(self) -> bytes:
+        """Allocate / reset this rank's exchange buffer and return its 64-byte CUDA IPC handle."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self._lib.myzkp_peer_export(self.h, _ptr(h)))
+        return h.tobytes()
+
+    def peer_attach(self, rank: int, world: int, handles: bytes):
+        """handles: the world's 64-byte handles concatenated in rank order."""
+        if len(handles) != 64 * world:
+            raise ValueError("need one 64-byte handle per rank")
+        a = np.frombuffer(handles, dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_peer_attach(self.h, rank, world, _ptr(a)))
+
+    def peer_attach_local(self, rank: int, ctxs):
+        """Contexts of one process (each already peer_export()ed), in rank order."""
+        arr = (ctypes.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        self._ck(self._lib.myzkp_peer_attach_local(self.h, rank, len(ctxs), arr))
+
+    def peer_detach(self):
+        self._ck(self._lib.myzkp_peer_detach(self.h))
+
+    def peer_set_timeout_ms(self, ms: int):
+        self._ck(self._lib.myzkp_peer_set_timeout_ms(self.h, ms))
+
+    def commit_sharded_dev(self, d_scalars: int, n_local: int, d_out_c64: int):
+        self._ck(self._lib.myzkp_kzg_commit_sharded_dev(self.h, ctypes.c_void_p(d_scalars), n_local, ctypes.c_void_p(d_out_c64)))
+
+    def exchange_sum_dev(self, d_partial_xyzz128: int, d_out_c64: int):
+        self._ck(self._lib.myzkp_g1_exchange_sum_dev(self.h, ctypes.c_void_p(d_partial_xyzz128), ctypes.c_void_p(d_out_c64)))
+
+    def commit_sharded(self, scalars: np.ndarray):
+        """Host scalars of this rank's range -> the whole polynomial's commitment (synchronous)."""
+        a = scalars_to_bytes(scalars)
+        out = np.zeros(64, dtype=np.uint8)
+        self._ck(self._lib.myzkp_kzg_commit_sharded(self.h, _ptr(a), a.shape[0], _ptr(out)))
+        return point_from_bytes(out.tobytes())
+
+    def open_sharded_dev(self, d_coefs: int, n_local: int, u: int, d_out_y32: int, d_out_w64: int):
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_kzg_open_sharded_dev(self.h, ctypes.c_void_p(d_coefs), n_local, _ptr(ub),
+                                                      ctypes.c_void_p(d_out_y32), ctypes.c_void_p(d_out_w64)))
+
+    for f in (commit_dev, open_dev, msm_partial_dev, msm_partial_host, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev,
+              peer_export, peer_attach, peer_attach_local, peer_detach, peer_set_timeout_ms, commit_sharded_dev,
+              exchange_sum_dev, commit_sharded, open_sharded_dev):
         setattr(Context, f.__name__, f)
 
 

@@ -213,6 +213,7 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   }
   ctx->children.clear();
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  peer_release(ctx);
   free_ctx_scratch(ctx);
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
     for (int i = 0; i < 6; i++)
@@ -240,7 +241,7 @@ int myzkp_ctx_sync(myzkp_ctx* ctx) {
   if (!ctx) return MYZKP_ERR_INVALID_ARG;
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  return MYZKP_OK;
+  return peer_check(ctx);
 }
 
 const char* myzkp_last_error(const myzkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
@@ -319,6 +320,57 @@ int myzkp_g1_msm_partial(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n, si
   MZ_TRY(enqueue_chunk_uploads(ctx, scalars_le, ctx->scalars.as<uint8_t>(), n, K, false));
   return chunked_msm(ctx, ctx->scalars.as<uint32_t>(), n, K, false, nullptr, nullptr, static_cast<XYZZ*>(d_out_xyzz128),
                      srs_off);
+}
+
+// ---- range-sharded commit / open with the exchange fused over peer memory (peer.cu) -------------
+int myzkp_kzg_commit_sharded_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n_local, void* d_out_c64) {
+  if (!ctx || (!d_scalars && n_local) || !d_out_c64) return MYZKP_ERR_INVALID_ARG;
+  MZ_TRY(begin_call(ctx));
+  XYZZ* res = reinterpret_cast<XYZZ*>(ctx->small.as<uint8_t>() + kSmallXyzz);
+  MZ_TRY(msm_xyzz(ctx, static_cast<const uint32_t*>(d_scalars), n_local, 0, res));
+  return peer_exchange(ctx, 0, res, 128, d_out_c64, nullptr);
+}
+
+int myzkp_g1_exchange_sum_dev(myzkp_ctx* ctx, const void* d_partial_xyzz128, void* d_out_c64) {
+  if (!ctx || !d_partial_xyzz128 || !d_out_c64) return MYZKP_ERR_INVALID_ARG;
+  MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return peer_exchange(ctx, 0, d_partial_xyzz128, 128, d_out_c64, nullptr);
+}
+
+int myzkp_kzg_commit_sharded(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n_local, uint8_t out_c[64]) {
+  if (!ctx || (!scalars_le && n_local) || !out_c) return MYZKP_ERR_INVALID_ARG;
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  MZ_TRY(myzkp_g1_msm_partial(ctx, scalars_le, n_local, 0, s + kSmallXyzz));
+  MZ_TRY(peer_exchange(ctx, 0, s + kSmallXyzz, 128, s + kSmallPoint, nullptr));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_c, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_TRY(end_call_check_flag(ctx));
+  return peer_check(ctx);
+}
+
+int myzkp_kzg_open_sharded_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n_local, const uint8_t u_le[32],
+                               void* d_out_y32, void* d_out_w64) {
+  if (!ctx || (!d_coefs && n_local) || !u_le || !d_out_y32 || !d_out_w64) return MYZKP_ERR_INVALID_ARG;
+  if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
+  MZ_TRY(begin_call(ctx));
+  uint8_t* s = ctx->small.as<uint8_t>();
+  const uint32_t* coefs = static_cast<const uint32_t*>(d_coefs);
+  uint32_t* pair = reinterpret_cast<uint32_t*>(s + kSmallY);         // (h, u^n) of this range
+  uint32_t* carry = reinterpret_cast<uint32_t*>(s + kSmallY + 64);   // carry entering from above
+  XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);               // partial, then c_0 right behind it
+  uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallXyzz + sizeof(XYZZ));
+  if (n_local) MZ_TRY(fr_check_canonical(ctx, coefs, n_local, reinterpret_cast<int*>(s + kSmallFlag)));
+  MZ_TRY(fr_range_eval(ctx, coefs, n_local, u_le, pair, pair + 8));
+  MZ_TRY(peer_exchange(ctx, 1, pair, 64, carry, nullptr));
+  if (n_local) {
+    MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n_local * 32));
+    MZ_TRY(fr_range_quotient(ctx, coefs, n_local, u_le, nullptr, ctx->scalars2.as<uint32_t>(), c0, carry));
+  } else {
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(c0, carry, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  // q_{lo+i} pairs with local SRS point i (the global top quotient coefficient is the zero carry)
+  MZ_TRY(msm_xyzz(ctx, ctx->scalars2.as<uint32_t>(), n_local, 0, res));
+  return peer_exchange(ctx, 0, res, 160, d_out_w64, d_out_y32);
 }
 
 int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64) {

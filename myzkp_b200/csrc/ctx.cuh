@@ -99,6 +99,16 @@ struct myzkp_ctx {
   cudaEvent_t copy_ev[8] = {};
   cudaEvent_t copy_done_ev = nullptr;
 
+  // peer-memory exchange of the range-sharded multi-GPU path (peer.cu): one small buffer per
+  // rank, mapped into every peer (CUDA IPC between processes, plain pointers inside one)
+  static constexpr int kMaxPeers = 16;
+  uint8_t* peer_local = nullptr;
+  uint8_t* peer_bufs[kMaxPeers] = {};
+  bool peer_ipc[kMaxPeers] = {};
+  int peer_rank = -1, peer_world = 0;
+  uint32_t peer_epoch = 0;
+  unsigned long long peer_timeout_ns = 10ull * 1000 * 1000 * 1000;
+
   // optional per-phase CUDA-event timing of the last MSM (bench.py roofline)
   // phases: 0 recode, 1 sort, 2 accumulate, 3 merge heads, 4 bucket reduce + tree sum
   // a ring of kPhaseSlots MSM calls so a timed loop can be read back after its final sync
@@ -153,6 +163,11 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out);
 // XYZZ (device) -> canonical affine 64 B (device)
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
 int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);
+// peer.cu: fused exchange (+ sum / carry composition) over peer memory.  mode 0: XYZZ partials ->
+// affine bytes in d_out0 (and rank 0's 32 B tail in d_out1); mode 1: (h, u^n) pairs -> carry in d_out0
+int peer_exchange(myzkp_ctx* ctx, int mode, const void* d_payload, int bytes, void* d_out0, void* d_out1);
+int peer_check(myzkp_ctx* ctx);
+void peer_release(myzkp_ctx* ctx);
 
 // ---- baa.cu ----
 int baa_accumulate(myzkp_ctx* ctx, const uint32_t* keys_s, const uint32_t* vals_s, uint64_t M, uint32_t L,

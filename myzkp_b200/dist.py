@@ -12,6 +12,14 @@ range to (h_g, u^{n_g}); after one all-gather of 64 B per rank every rank compos
 the carry entering its range from above on the host (world_size field ops) and
 runs the local scan; the quotient slice then feeds the same sharded MSM.
 
+Exchange: by default (`DeviceOps.attach_peers`) the partials never go through a
+collective library.  Each rank's 8 KiB exchange buffer is mapped into every peer
+(CUDA IPC; the 64-byte handles are swapped once with torch.distributed) and the
+commit / open end in ONE kernel that stores the 128-byte partial into all peers'
+HBM over NVLink, waits for theirs and sums + normalises in the same launch
+(csrc/peer.cu).  The all_gather(NCCL) + sum path stays as the portable route and is
+what the gloo CPU tests drive.
+
 The group-element arithmetic is behind an `ops` object: `DeviceOps` drives the
 CUDA library; the CPU tests (gloo, world_size 2) plug the oracle in to check the
 sharding arithmetic and the collective plumbing without a GPU.
@@ -55,6 +63,40 @@ class DeviceOps:
         self.pair = torch.zeros(64, dtype=torch.uint8, device=device)  # (h, u^n)
         self.c0 = torch.zeros(32, dtype=torch.uint8, device=device)
         self.q = None
+
+    def attach_peers(self, rank: int, world: int, group=None) -> bool:
+        """Map every rank's exchange buffer (handles swapped through torch.distributed).  Returns
+        False (and leaves the NCCL route in place) if any rank could not map its peers."""
+        handle = self.ctx.peer_export()
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.device)
+        allh = torch.zeros(64 * world, dtype=torch.uint8, device=self.device)
+        if world > 1:
+            dist.all_gather_into_tensor(allh, mine, group=group)
+        else:
+            allh.copy_(mine)
+        ok = 1
+        try:
+            self.ctx.peer_attach(rank, world, allh.cpu().numpy().tobytes())
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.fused = bool(int(flag.item()))
+        if not self.fused:
+            self.ctx.peer_detach()
+        return self.fused
+
+    fused = False
+
+    def commit_fused(self, d_scalars: int, n: int, out64: torch.Tensor) -> None:
+        self.ctx.commit_sharded_dev(d_scalars, n, out64.data_ptr())
+
+    def exchange_sum(self, partial: torch.Tensor, out64: torch.Tensor) -> None:
+        self.ctx.exchange_sum_dev(partial.data_ptr(), out64.data_ptr())
+
+    def open_fused(self, d_coefs: int, n: int, u: int, out_y32: torch.Tensor, out_w64: torch.Tensor) -> None:
+        self.ctx.open_sharded_dev(d_coefs, n, u, out_y32.data_ptr(), out_w64.data_ptr())
 
     def msm_partial(self, d_scalars: int, n: int) -> torch.Tensor:
         self.ctx.msm_partial_dev(d_scalars, n, 0, self.partial.data_ptr())
@@ -101,6 +143,8 @@ class ShardedKZG:
     def commit(self, d_scalars_local: int, out64: torch.Tensor, n_local: int = None) -> None:
         """d_scalars_local: this rank's coefficient slice [lo, hi) (device address)."""
         n = self.n_local if n_local is None else n_local
+        if getattr(self.ops, "fused", False):
+            return self.ops.commit_fused(d_scalars_local, n, out64)
         partial = self.ops.msm_partial(d_scalars_local, n)
         gathered = self._all_gather(partial, "_gather128")
         self.ops.sum_partials(gathered, self.world, out64)
@@ -108,11 +152,15 @@ class ShardedKZG:
     def commit_host(self, host_scalars_local, out64: torch.Tensor) -> None:
         """Same with this rank's coefficient slice in host (pinned) memory: upload pipelined with the MSM."""
         partial = self.ops.msm_partial_host(host_scalars_local, self.n_local)
+        if getattr(self.ops, "fused", False):
+            return self.ops.exchange_sum(partial, out64)
         gathered = self._all_gather(partial, "_gather128")
         self.ops.sum_partials(gathered, self.world, out64)
 
     def open(self, d_coefs_local: int, u: int, out_y32: torch.Tensor, out_w64: torch.Tensor) -> None:
         """open_kzg over the sharded polynomial: every rank ends with (y, W)."""
+        if getattr(self.ops, "fused", False):
+            return self.ops.open_fused(d_coefs_local, self.n_local, u, out_y32, out_w64)
         pair = self.ops.range_eval(d_coefs_local, self.n_local, u)
         g = self._all_gather(pair, "_gather64").cpu().numpy().tobytes()
         hs = [int.from_bytes(g[64 * r : 64 * r + 32], "little") for r in range(self.world)]

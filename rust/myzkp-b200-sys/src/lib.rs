@@ -58,6 +58,17 @@ extern "C" {
                                     d_out_xyzz128: *mut c_void) -> c_int;
     pub fn myzkp_g1_msm_partial(ctx: *mut myzkp_ctx, scalars_le: *const u8, n: usize, srs_off: usize,
                                 d_out_xyzz128: *mut c_void) -> c_int;
+    pub fn myzkp_peer_export(ctx: *mut myzkp_ctx, out_handle: *mut u8) -> c_int;
+    pub fn myzkp_peer_attach(ctx: *mut myzkp_ctx, rank: c_int, world: c_int, handles: *const u8) -> c_int;
+    pub fn myzkp_peer_attach_local(ctx: *mut myzkp_ctx, rank: c_int, world: c_int, ctxs: *const *mut myzkp_ctx) -> c_int;
+    pub fn myzkp_peer_detach(ctx: *mut myzkp_ctx) -> c_int;
+    pub fn myzkp_peer_set_timeout_ms(ctx: *mut myzkp_ctx, ms: u32) -> c_int;
+    pub fn myzkp_kzg_commit_sharded_dev(ctx: *mut myzkp_ctx, d_scalars: *const c_void, n_local: usize,
+                                        d_out_c64: *mut c_void) -> c_int;
+    pub fn myzkp_g1_exchange_sum_dev(ctx: *mut myzkp_ctx, d_partial_xyzz128: *const c_void, d_out_c64: *mut c_void) -> c_int;
+    pub fn myzkp_kzg_commit_sharded(ctx: *mut myzkp_ctx, scalars_le: *const u8, n_local: usize, out_c: *mut u8) -> c_int;
+    pub fn myzkp_kzg_open_sharded_dev(ctx: *mut myzkp_ctx, d_coefs: *const c_void, n_local: usize, u_le: *const u8,
+                                      d_out_y32: *mut c_void, d_out_w64: *mut c_void) -> c_int;
     pub fn myzkp_g1_sum_partials_dev(ctx: *mut myzkp_ctx, d_partials: *const c_void, k: usize,
                                      d_out_c64: *mut c_void) -> c_int;
     pub fn myzkp_fr_range_eval_dev(ctx: *mut myzkp_ctx, d_coefs: *const c_void, n: usize, u_le: *const u8,

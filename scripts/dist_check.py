@@ -28,19 +28,34 @@ for n in (1 << 16, (1 << 14) + 3, 5):
     lo, hi = shard_range(n, rank, world)
     ctx.srs_generate(alpha, hi - lo, first=lo)
     d = torch.from_numpy(coefs[lo:hi].view(np.int64).reshape(-1).copy()).to(dev) if hi > lo else torch.zeros(4, dtype=torch.int64, device=dev)
-    prover = ShardedKZG(DeviceOps(ctx, dev), rank, world, n)
-    out = torch.zeros(64, dtype=torch.uint8, device=dev)
-    y = torch.zeros(32, dtype=torch.uint8, device=dev)
-    w = torch.zeros(64, dtype=torch.uint8, device=dev)
-    prover.commit(d.data_ptr(), out)
-    prover.open(d.data_ptr(), u, y, w)
-    torch.cuda.synchronize()
     ints = synth.limbs_to_ints(coefs)
-    c = mz.context.point_from_bytes(out.cpu().numpy().tobytes())
-    yy = int.from_bytes(y.cpu().numpy().tobytes(), "little")
-    ww = mz.context.point_from_bytes(w.cpu().numpy().tobytes())
-    good = c == orc.expected_commit(ints, alpha) and (yy, ww) == orc.expected_open(ints, u, alpha)
-    ok = ok and good
-    print(f"rank {rank}/{world} n={n}: sharded commit+open {'OK' if good else 'MISMATCH'}", flush=True)
+    exp_c, exp_o = orc.expected_commit(ints, alpha), orc.expected_open(ints, u, alpha)
+    for route in ("nccl", "peer"):
+        ops = DeviceOps(ctx, dev)
+        if route == "peer" and not ops.attach_peers(rank, world):
+            print(f"rank {rank}/{world} n={n}: peer attach FAILED", flush=True)
+            ok = False
+            continue
+        prover = ShardedKZG(ops, rank, world, n)
+        for rep in range(2):
+            out = torch.zeros(64, dtype=torch.uint8, device=dev)
+            y = torch.zeros(32, dtype=torch.uint8, device=dev)
+            w = torch.zeros(64, dtype=torch.uint8, device=dev)
+            prover.commit(d.data_ptr(), out)
+            prover.open(d.data_ptr(), u, y, w)
+            ctx.sync()
+            torch.cuda.synchronize()
+            c = mz.context.point_from_bytes(out.cpu().numpy().tobytes())
+            yy = int.from_bytes(y.cpu().numpy().tobytes(), "little")
+            ww = mz.context.point_from_bytes(w.cpu().numpy().tobytes())
+            good = c == exp_c and (yy, ww) == exp_o
+            if route == "peer" and hi > lo:
+                good = good and ctx.commit_sharded(coefs[lo:hi]) == exp_c
+            elif route == "peer":
+                good = good and ctx.commit_sharded(coefs[:0]) == exp_c
+            ok = ok and good
+        print(f"rank {rank}/{world} n={n}: sharded commit+open via {route} {'OK' if good else 'MISMATCH'}", flush=True)
+    ctx.peer_detach()
+    dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -248,6 +248,80 @@ def test_sharded_commit_and_open_emulated_ranks(ctx):
         c.close()
 
 
+@pytest.mark.parametrize("n,world", [(3001, 3), (4, 5), (777, 1), (20000, 8)])
+def test_sharded_fused_peer_exchange_emulated_ranks(ctx, n, world):
+    """commit / open with the exchange fused over peer memory (csrc/peer.cu): one Context (own
+    stream) per emulated rank in this process, buffers attached by pointer; every rank must end
+    with the oracle's commitment and (y, W).  Run twice so both epoch parities are exercised."""
+    import torch
+
+    from myzkp_b200.dist import shard_range
+
+    alpha, u = 0xABCDEF0123456789ABCDEF, 0x1122334455667788
+    coefs = synth.random_scalars(n, 70 + n)
+    ints = synth.limbs_to_ints(coefs)
+    dev = torch.device("cuda", 0)
+    d_all = torch.from_numpy(coefs.view(np.int64).reshape(-1).copy()).to(dev)
+    ranks = []
+    for r in range(world):
+        c = mz.Context(0)
+        lo, hi = shard_range(n, r, world)
+        c.srs_generate(alpha, hi - lo, first=lo)
+        c.peer_export()
+        c.peer_set_timeout_ms(4000)
+        ranks.append((c, lo, hi))
+    ctxs = [c for c, _, _ in ranks]
+    outs = torch.zeros(world, 64, dtype=torch.uint8, device=dev)
+    ys = torch.zeros(world, 32, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(world, 64, dtype=torch.uint8, device=dev)
+    scratch = torch.zeros(128, dtype=torch.uint8, device=dev)
+    try:
+        for r, (c, lo, hi) in enumerate(ranks):
+            c.peer_attach_local(r, ctxs)
+            # grow the scratch buffers now: a cudaFree while a peer's exchange kernel spins would stall
+            c.msm_partial_dev(d_all.data_ptr() + lo * 32, hi - lo, 0, scratch.data_ptr())
+            c.open_dev(d_all.data_ptr() + lo * 32, hi - lo, u, scratch.data_ptr(), scratch.data_ptr() + 32)
+            c.sync()
+        exp_c = o.expected_commit(ints, alpha)
+        exp_y, exp_w = o.expected_open(ints, u, alpha)
+        for _ in range(2):
+            outs.zero_(); ys.zero_(); ws.zero_()
+            torch.cuda.synchronize()
+            for r, (c, lo, hi) in enumerate(ranks):
+                c.commit_sharded_dev(d_all.data_ptr() + lo * 32, hi - lo, outs[r].data_ptr())
+                c.open_sharded_dev(d_all.data_ptr() + lo * 32, hi - lo, u, ys[r].data_ptr(), ws[r].data_ptr())
+            for c in ctxs:
+                c.sync()
+            for r in range(world):
+                assert mz.context.point_from_bytes(outs[r].cpu().numpy().tobytes()) == exp_c
+                assert int.from_bytes(ys[r].cpu().numpy().tobytes(), "little") == exp_y
+                assert mz.context.point_from_bytes(ws[r].cpu().numpy().tobytes()) == exp_w
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_exchange_timeout_is_reported(ctx):
+    """A rank whose peer never shows up gives up after the timeout and the next sync reports it."""
+    import torch
+
+    a, b = mz.Context(0), mz.Context(0)
+    try:
+        for c in (a, b):
+            c.srs_generate(5, 4)
+            c.peer_export()
+            c.peer_set_timeout_ms(200)
+        a.peer_attach_local(0, [a, b])
+        b.peer_attach_local(1, [a, b])
+        d = torch.zeros(4 * 4, dtype=torch.int64, device="cuda:0")
+        out = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
+        a.commit_sharded_dev(d.data_ptr(), 4, out.data_ptr())  # b never calls
+        with pytest.raises(mz.MyzkpError):
+            a.sync()
+    finally:
+        a.close(); b.close()
+
+
 def test_chunked_upload_pipeline(ctx):
     """Host-buffer commit/open split into upload chunks (auto from 2^23) - forced here at a small size."""
     n = 5003

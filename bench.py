@@ -239,6 +239,18 @@ def main():
         if not verified:
             raise SystemExit(f"bench.py: commitment mismatch vs oracle expected value at 2^{log2n}")
 
+    tiny = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def align():
+        """After the host barrier the ranks' streams are still skewed by the barrier's wake-up jitter
+        (milliseconds with 8 processes); a device-side rendezvous right before the start event makes the
+        timed regions begin together, so that skew is not billed to the first step."""
+        if world > 1:
+            if ops.fused:
+                ops.exchange_sum(ops.partial, out)
+            else:
+                dist.all_reduce(tiny)
+
     # ---- value: device-resident scalars ------------------------------------------------
     ctx.enable_phase_timing(True)
     for _ in range(args.warmup):
@@ -248,6 +260,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align()
     e0.record()
     for _ in range(args.steps):
         step_resident()
@@ -274,6 +287,7 @@ def main():
     for _ in range(2):
         step_e2e()
     barrier()
+    align()
     e0.record()
     for _ in range(args.steps):
         res = step_e2e()

@@ -366,14 +366,13 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
   // head that msm_merge_heads must fold in serially.
   uint32_t L = (uint32_t)ctx->segment_len;
   if (L == 0) {
-    uint64_t target_threads = (uint64_t)ctx->sm_count * 512 * 8;
+    // Measured on B200 (profiles/phase_sweep_r1d.json): the head merge costs ~0.64 ns per
+    // segment while doubling L slows the accumulate by ~2 %, so aim at four waves of
+    // resident threads (~300 k segments) with L between 32 (16 for tiny inputs) and 256.
+    uint64_t target_threads = (uint64_t)ctx->sm_count * 512 * 4;
     uint64_t l = (M + target_threads - 1) / target_threads;
-    uint64_t avg_run = M / nb;
-    uint64_t l_run = avg_run / 2;                 // ~2 heads per bucket ...
-    uint64_t l_fill = M / (128 * 1024);           // ... but keep >= ~128 k segments in flight
-    if (l_run > l_fill) l_run = l_fill;
-    if (l < l_run) l = l_run;
-    L = (uint32_t)(l < 8 ? 8 : (l > 256 ? 256 : l));
+    const uint64_t l_min = M >= ((uint64_t)1 << 19) ? 32 : 16;
+    L = (uint32_t)(l < l_min ? l_min : (l > 256 ? 256 : l));
     // quantise to whole waves of resident blocks (4 blocks of 128 threads per SM) so
     // the last wave is not half empty
     const uint64_t wave = (uint64_t)ctx->sm_count * 4 * kAccThreads;

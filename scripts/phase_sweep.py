@@ -17,13 +17,15 @@ out = torch.zeros(64, dtype=torch.uint8, device="cuda")
 res = []
 spec = sys.argv[1:] or ["16:0,12,16", "20:0,16,20", "22:0,16,20,24"]
 for item in spec:
-    lg, wbs = item.split(":")
+    parts = item.split(":")  # log2n : window bits list [: segment length list]
+    lg, wbs = parts[0], parts[1]
+    segs = [int(x) for x in parts[2].split(",")] if len(parts) > 2 else [0]
     lg = int(lg)
     n = 1 << lg
     ctx.srs_generate(alpha, n)
     coefs = torch.from_numpy(synth.random_scalars(n, synth.SEED_SCALARS + lg).view(np.int64).reshape(-1)).cuda()
     for wb in [int(x) for x in wbs.split(",")]:
-        for seg in ([0] if len(sys.argv) < 99 else [0]):
+        for seg in segs:
             ctx.set_msm_params(wb, seg)
             for _ in range(3):
                 ctx.commit_dev(coefs.data_ptr(), n, out.data_ptr())

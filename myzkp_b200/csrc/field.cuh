@@ -308,8 +308,130 @@ MZ_HD Fe<PR> fe_mul(const Fe<PR>& a, const Fe<PR>& b) {
   return r;
 }
 
+// --- Montgomery square --------------------------------------------------------
+// a^2 costs 36 wide products instead of 64: the 28 products a_i*a_j (i < j) are summed once
+// and doubled, the 8 squares a_i^2 are added on top.  The 512-bit result S is then reduced
+// by 8 rows of m*modulus (the second half of mont_row; with no a*b_i products the shift of
+// the even array rides on the odd-limb products of m*modulus), and S's high half is added
+// at the end: 100 wide multiplies against 128 for fe_mul.
+//
+// Off-diagonal sum T, in two accumulators so every row is one carry chain per parity:
+//   X[k] = column k+1: products whose low column i+j is odd   (columns 1..14)
+//   Y[k] = column k+2: products whose low column i+j is even  (columns 2..13)
+// A chain that ends on a column an earlier row already wrote may carry out; the next
+// column is untouched at that point and receives the carry bit.  A chain that ends on
+// an untouched column adds hi(product) <= 2^32 - 2 to zero and cannot carry out.
+namespace detail {
+MZ_HD uint32_t shl1(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
+
+// one reduction row without multiplicand products: (E, O) are the previous row's (odd, even) arrays
 template <class PR>
-MZ_HD Fe<PR> fe_sqr(const Fe<PR>& a) { return fe_mul(a, a); }
+MZ_HD void redc_row(uint32_t* E, uint32_t* O) {
+  E[0] = add_cc(E[0], O[1]);
+  uint32_t m = mul_lo(E[0], PR::INV);
+  row_shift_mad_odd(O, ModAcc<PR>(), m);
+  row_mad_even(E, ModAcc<PR>(), m);
+  O[7] = addc(O[7], 0);
+}
+}  // namespace detail
+
+template <class PR>
+MZ_HD Fe<PR> fe_sqr(const Fe<PR>& a) {
+  const uint32_t* v = a.v;
+  uint32_t X[14], Y[12];
+  // row 0: a0 * a[1..7]
+  mul_wide(v[0], v[1], X[0], X[1]);
+  mul_wide(v[0], v[3], X[2], X[3]);
+  mul_wide(v[0], v[5], X[4], X[5]);
+  mul_wide(v[0], v[7], X[6], X[7]);
+  mul_wide(v[0], v[2], Y[0], Y[1]);
+  mul_wide(v[0], v[4], Y[2], Y[3]);
+  mul_wide(v[0], v[6], Y[4], Y[5]);
+  // row 1: a1 * a[2..7]   X: columns (3,4),(5,6),(7,8) all written -> carry to column 9
+  X[2] = mad_lo_cc(v[1], v[2], X[2]);  X[3] = madc_hi_cc(v[1], v[2], X[3]);
+  X[4] = madc_lo_cc(v[1], v[4], X[4]); X[5] = madc_hi_cc(v[1], v[4], X[5]);
+  X[6] = madc_lo_cc(v[1], v[6], X[6]); X[7] = madc_hi_cc(v[1], v[6], X[7]);
+  X[8] = addc(0, 0);
+  //                        Y: columns (4,5),(6,7),(8,9); (8,9) new
+  Y[2] = mad_lo_cc(v[1], v[3], Y[2]);  Y[3] = madc_hi_cc(v[1], v[3], Y[3]);
+  Y[4] = madc_lo_cc(v[1], v[5], Y[4]); Y[5] = madc_hi_cc(v[1], v[5], Y[5]);
+  Y[6] = madc_lo_cc(v[1], v[7], 0);    Y[7] = madc_hi(v[1], v[7], 0);
+  // row 2: a2 * a[3..7]   X: (5,6),(7,8),(9,10); column 9 holds a carry bit, 10 is new
+  X[4] = mad_lo_cc(v[2], v[3], X[4]);  X[5] = madc_hi_cc(v[2], v[3], X[5]);
+  X[6] = madc_lo_cc(v[2], v[5], X[6]); X[7] = madc_hi_cc(v[2], v[5], X[7]);
+  X[8] = madc_lo_cc(v[2], v[7], X[8]); X[9] = madc_hi(v[2], v[7], 0);
+  //                        Y: (6,7),(8,9) written -> carry to column 10
+  Y[4] = mad_lo_cc(v[2], v[4], Y[4]);  Y[5] = madc_hi_cc(v[2], v[4], Y[5]);
+  Y[6] = madc_lo_cc(v[2], v[6], Y[6]); Y[7] = madc_hi_cc(v[2], v[6], Y[7]);
+  Y[8] = addc(0, 0);
+  // row 3: a3 * a[4..7]   X: (7,8),(9,10) written -> carry to column 11
+  X[6] = mad_lo_cc(v[3], v[4], X[6]);  X[7] = madc_hi_cc(v[3], v[4], X[7]);
+  X[8] = madc_lo_cc(v[3], v[6], X[8]); X[9] = madc_hi_cc(v[3], v[6], X[9]);
+  X[10] = addc(0, 0);
+  //                        Y: (8,9),(10,11); column 10 holds a carry bit, 11 is new
+  Y[6] = mad_lo_cc(v[3], v[5], Y[6]);  Y[7] = madc_hi_cc(v[3], v[5], Y[7]);
+  Y[8] = madc_lo_cc(v[3], v[7], Y[8]); Y[9] = madc_hi(v[3], v[7], 0);
+  // row 4: a4 * a[5..7]   X: (9,10),(11,12); 12 new
+  X[8] = mad_lo_cc(v[4], v[5], X[8]);    X[9] = madc_hi_cc(v[4], v[5], X[9]);
+  X[10] = madc_lo_cc(v[4], v[7], X[10]); X[11] = madc_hi(v[4], v[7], 0);
+  //                        Y: (10,11) written -> carry to column 12
+  Y[8] = mad_lo_cc(v[4], v[6], Y[8]);  Y[9] = madc_hi_cc(v[4], v[6], Y[9]);
+  Y[10] = addc(0, 0);
+  // row 5: a5 * a[6..7]   X: (11,12) written -> carry to column 13
+  X[10] = mad_lo_cc(v[5], v[6], X[10]); X[11] = madc_hi_cc(v[5], v[6], X[11]);
+  X[12] = addc(0, 0);
+  //                        Y: (12,13); 13 new
+  Y[10] = mad_lo_cc(v[5], v[7], Y[10]); Y[11] = madc_hi(v[5], v[7], 0);
+  // row 6: a6 * a7        X: (13,14); 14 new
+  X[12] = mad_lo_cc(v[6], v[7], X[12]); X[13] = madc_hi(v[6], v[7], 0);
+
+  // T = X * 2^32 + Y * 2^64 (columns 1..15)
+  uint32_t T[16];
+  T[0] = 0;
+  T[1] = X[0];
+  T[2] = add_cc(X[1], Y[0]);
+#pragma unroll
+  for (int k = 3; k < 14; k++) T[k] = addc_cc(X[k - 1], Y[k - 2]);
+  T[14] = addc_cc(X[13], 0);
+  T[15] = addc(0, 0);
+  // S = 2 T + sum_i a_i^2 2^(64 i): the doubling is a funnel shift, the squares ride one carry chain
+  uint32_t S[16];
+  S[0] = mad_lo_cc(v[0], v[0], 0);
+  S[1] = madc_hi_cc(v[0], v[0], detail::shl1(0, T[1]));
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    S[2 * i] = madc_lo_cc(v[i], v[i], detail::shl1(T[2 * i - 1], T[2 * i]));
+    S[2 * i + 1] = madc_hi_cc(v[i], v[i], detail::shl1(T[2 * i], T[2 * i + 1]));
+  }
+  // Montgomery reduction of the low half
+  uint32_t E[8], O[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { E[i] = S[i]; O[i] = 0; }
+  {
+    uint32_t m = mul_lo(E[0], PR::INV);
+    detail::row_mad_odd(O, detail::ModAcc<PR>(), m);
+    detail::row_mad_even(E, detail::ModAcc<PR>(), m);
+    O[7] = addc(O[7], 0);
+  }
+  detail::redc_row<PR>(O, E);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    detail::redc_row<PR>(E, O);
+    detail::redc_row<PR>(O, E);
+  }
+  Fe<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  // + high half of S (r < modulus + 2^252 < 2 * modulus)
+  r.v[0] = add_cc(r.v[0], S[8]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], S[8 + i]);
+  r.v[7] = addc(r.v[7], S[15]);
+  fe_reduce_once(r);
+  return r;
+}
 
 template <class PR>
 MZ_HD Fe<PR> fe_to_mont(const Fe<PR>& a) { return fe_mul(a, Fe<PR>::r2()); }

@@ -7,6 +7,7 @@ extern "C" {
 #define UN(name, T, fn) void name(const uint32_t* a, uint32_t* o) { T x; for (int i=0;i<8;i++){x.v[i]=a[i];} T r = fn(x); for(int i=0;i<8;i++) o[i]=r.v[i]; }
 BIN(emul_fq_mul, Fq, fe_mul) BIN(emul_fq_add, Fq, fe_add) BIN(emul_fq_sub, Fq, fe_sub)
 BIN(emul_fr_mul, Fr, fe_mul) BIN(emul_fr_add, Fr, fe_add) BIN(emul_fr_sub, Fr, fe_sub)
+UN(emul_fq_sqr, Fq, fe_sqr) UN(emul_fr_sqr, Fr, fe_sqr)
 UN(emul_fq_inv_bingcd, Fq, fe_inv_bingcd) UN(emul_fr_inv_bingcd, Fr, fe_inv_bingcd)
 UN(emul_fq_neg, Fq, fe_neg) UN(emul_fq_inv, Fq, fe_inv) UN(emul_fq_to_mont, Fq, fe_to_mont) UN(emul_fq_from_mont, Fq, fe_from_mont)
 UN(emul_fr_neg, Fr, fe_neg) UN(emul_fr_inv, Fr, fe_inv) UN(emul_fr_to_mont, Fr, fe_to_mont) UN(emul_fr_from_mont, Fr, fe_from_mont)

@@ -60,8 +60,14 @@ def test_field_ops(name, m):
             assert b2("add", x, y) == (x + y) % m
             assert b2("sub", x, y) == (x - y) % m
         assert u1("neg", x) == (-x) % m
+        assert u1("sqr", x) == x * x * rinv % m
         assert u1("to_mont", x) == x * RR % m
         assert u1("from_mont", x) == x * rinv % m
+    # the dedicated squaring: limb patterns that maximise carries, and a long random run
+    limbs = [0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF]
+    for _ in range(3000):
+        x = sum(rnd.choice(limbs) << (32 * i) for i in range(8)) % m if rnd.random() < 0.5 else rnd.randrange(m)
+        assert u1("sqr", x) == x * x * rinv % m
     for x in vals[:24]:
         exp = (pow(x, -1, m) if x else 0) * RR % m
         assert u1("inv", x * RR % m) == exp

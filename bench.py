@@ -343,7 +343,7 @@ def main():
             "executed_TIMAD_s": executed, "executed_frac": (executed / imad_peak) if imad_peak else None,
             "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step,
             "note": "achieved = points x 42240 algorithmic IMAD (SURVEY 8d, c=16 XYZZ) / accumulate time; executed = "
-                    "entries x %d IMAD actually issued (8M at 264 + 2S at 208; window c=%%d, %%d windows)" %% IMAD_PER_MADD %% (info.get("window_bits", 0), info.get("windows", 0)),
+                    "entries x %d IMAD actually issued (8M at 264 + 2S at 208; window c=%d, %d windows)" % (IMAD_PER_MADD, info.get("window_bits", 0), info.get("windows", 0)),
         }
         if sort_ms > 0 and peaks.get("hbm_gbs"):
             gbs = n_local * SORT_BYTES_PER_POINT / (sort_ms * 1e-3) / 1e9

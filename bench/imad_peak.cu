@@ -40,6 +40,50 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, uint32_t seed,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// other pipes, for planning: FP64 FMA (52-bit-limb multiplication candidates), integer adds, and
+// DFMA + mad.wide issued together (do the FP64 and IMAD pipes overlap?)
+//   MODE 0: fma.rn.f64   MODE 1: add.u32 (IADD3)   MODE 2: one fma.rn.f64 + one mad.wide.u32 per slot
+template <int MODE>
+__global__ void __launch_bounds__(256) pipe_kernel(uint32_t* out, uint32_t seed, int iters) {
+  double d[ILP], e = 1.0000001 + seed * 1e-12, f = 1e-9;
+  uint32_t a[ILP], b = seed | 1u;
+  uint64_t w[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) { d[i] = 1.0 + threadIdx.x * 1e-6 + i; a[i] = threadIdx.x + i + seed; w[i] = a[i]; }
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int i = 0; i < ILP; i++) {
+        if (MODE == 0 || MODE == 2) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(f));
+        if (MODE == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+        if (MODE == 2) {
+          uint32_t lo = (uint32_t)w[i];
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(lo), "r"(b));
+        }
+      }
+    }
+  }
+  double sd = 0;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) { sd += d[i]; s += a[i] + (uint32_t)w[i] + (uint32_t)(w[i] >> 32); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s + (uint32_t)__double2ll_rz(sd);
+}
+
+// dependent chain of Montgomery squarings
+__global__ void __launch_bounds__(128) fesqr_kernel(uint32_t* out, uint32_t seed, int iters) {
+  mz::Fq x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = seed * (i + 3) + threadIdx.x;
+  x.v[7] &= 0x0fffffff;
+  for (int k = 0; k < iters; k++) x = mz::fe_sqr(x);
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= x.v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // dependent chain(s) of Montgomery multiplies: CH independent chains per thread
 template <int CH>
 __global__ void __launch_bounds__(128) femul_kernel(uint32_t* out, uint32_t seed, int iters) {
@@ -106,6 +150,22 @@ int main() {
     float ms2 = time_ms([&] { femul_kernel<2><<<blocks, 128>>>(out, 999u, it); }, 5);
     printf(", \"femul_ch1_thr%d_Gmul\": %.2f", bps * 512, (double)blocks * 128 * it / (ms1 * 1e-3) / 1e9);
     printf(", \"femul_ch2_thr%d_Gmul\": %.2f", bps * 512, (double)blocks * 128 * it * 2 / (ms2 * 1e-3) / 1e9);
+  }
+  {
+    const char* pn[3] = {"dfma", "iadd", "dfma_plus_mad_wide_pairs"};
+    for (int mode = 0; mode < 3; mode++) {
+      int blocks = sms * 8;
+      float ms = 0;
+      if (mode == 0) ms = time_ms([&] { pipe_kernel<0><<<blocks, 256>>>(out, 12345u, iters); }, 5);
+      if (mode == 1) ms = time_ms([&] { pipe_kernel<1><<<blocks, 256>>>(out, 12345u, iters); }, 5);
+      if (mode == 2) ms = time_ms([&] { pipe_kernel<2><<<blocks, 256>>>(out, 12345u, iters); }, 5);
+      double ops = (double)blocks * 256 * iters * 8.0 * ILP;
+      printf(", \"%s_thr2048_Tops\": %.3f", pn[mode], ops / (ms * 1e-3) / 1e12);
+    }
+    int blocks = sms * 16;
+    const int it = 2000;
+    float ms = time_ms([&] { fesqr_kernel<<<blocks, 128>>>(out, 999u, it); }, 5);
+    printf(", \"fesqr_ch1_thr2048_Gsqr\": %.2f", (double)blocks * 128 * it / (ms * 1e-3) / 1e9);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf(", \"status\": \"%s\"}\n", cudaGetErrorString(e));

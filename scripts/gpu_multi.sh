@@ -7,9 +7,9 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
    scripts/dist_check.py 2>&1 | grep -E "rank|Error|error" | tee gpurun_out/dist_check_n$N.txt
 if [ "$2" = "both" ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
-   bench.py --gpus $N --steps 5 --warmup 3 --exchange nccl > gpurun_out/bench_n${N}_nccl.json 2> gpurun_out/bench_n${N}_nccl.err
+   bench.py --gpus $N --steps 10 --warmup 3 --exchange nccl > gpurun_out/bench_n${N}_nccl.json 2> gpurun_out/bench_n${N}_nccl.err
 grep -o '"ms_per_step": [0-9.]*\|"exchange_ms": [0-9.]*' gpurun_out/bench_n${N}_nccl.json
 fi
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-   bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+   bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 tail -3 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json

@@ -71,11 +71,40 @@ inline ProofKZG open_kzg(const Polynomial& f, const Scalar& u, const PublicKeyKZ
                           p.w.xy.data()));
   return p;
 }
-// commit_gemini (gemini.rs:112-114)
+// commit_gemini (gemini.rs:112-114): one batched call
 inline std::vector<CommitmentKZG> commit_gemini(const std::vector<Polynomial>& polys, const PublicKeyKZG& pk) {
-  std::vector<CommitmentKZG> out;
-  for (const auto& p : polys) out.push_back(commit_kzg(p, pk));
+  std::vector<const uint8_t*> ptrs;
+  std::vector<size_t> lens;
+  for (const auto& p : polys) {
+    ptrs.push_back(p.coef.empty() ? nullptr : p.coef[0].data());
+    lens.push_back(p.coef.size());
+  }
+  std::vector<CommitmentKZG> out(polys.size());
+  if (!polys.empty()) pk.check(myzkp_kzg_commit_batch(pk.ctx(), ptrs.data(), lens.data(), polys.size(), out[0].xy.data()));
   return out;
+}
+
+// ---- range-sharded prover: one PublicKeyKZG per GPU, rank g holding powers_1[first, first + count) ----
+inline void setup_kzg_range(PublicKeyKZG& pk, size_t first, size_t count, const Scalar& alpha) {
+  pk.check(myzkp_srs_generate_g1(pk.ctx(), alpha.data(), first, count));
+}
+// all ranks live in this process: map every rank's exchange buffer into every other (csrc/peer.cu)
+inline void attach_peers(const std::vector<PublicKeyKZG*>& ranks) {
+  std::vector<myzkp_ctx*> ctxs;
+  for (auto* r : ranks) {
+    r->check(myzkp_peer_export(r->ctx(), nullptr));
+    ctxs.push_back(r->ctx());
+  }
+  for (size_t g = 0; g < ranks.size(); g++)
+    ranks[g]->check(myzkp_peer_attach_local(ranks[g]->ctx(), (int)g, (int)ranks.size(), ctxs.data()));
+}
+// commit_kzg of the whole polynomial from this rank's coefficient slice; every rank returns the same point.
+// Blocks until the peers have called it too: drive each rank from its own host thread.
+inline CommitmentKZG commit_kzg_sharded(const Polynomial& local_slice, const PublicKeyKZG& pk) {
+  G1Point c;
+  pk.check(myzkp_kzg_commit_sharded(pk.ctx(), local_slice.coef.empty() ? nullptr : local_slice.coef[0].data(),
+                                    local_slice.coef.size(), c.xy.data()));
+  return c;
 }
 
 }  // namespace myzkp_b200

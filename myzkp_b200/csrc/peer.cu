@@ -153,7 +153,8 @@ int peer_exchange(myzkp_ctx* ctx, int mode, const void* d_payload, int bytes, vo
 int peer_check(myzkp_ctx* ctx) {
   if (!ctx->peer_local || ctx->peer_world <= 0) return MYZKP_OK;
   int h = 0;
-  MZ_CUDA_TRY(ctx, cudaMemcpy(&h, ctx->peer_local + kPeerErrOff, sizeof h, cudaMemcpyDeviceToHost));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctx->peer_local + kPeerErrOff, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (h) return fail(ctx, MYZKP_ERR_CUDA, "peer exchange timed out waiting for another rank");
   return MYZKP_OK;
 }

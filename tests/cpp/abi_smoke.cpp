@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "myzkp_b200.hpp"
 
@@ -40,6 +41,30 @@ int main() {
     bool threw = false;
     try { commit_kzg(too_long, pk); } catch (const std::runtime_error&) { threw = true; }
     if (!threw) { printf("FAIL no error for deg > max_d\n"); return 1; }
+    // commit_gemini: one batched call, same points as one commit per polynomial
+    Polynomial g;
+    for (uint64_t v : {7, 0, 5}) g.coef.push_back(scalar_u64(v));
+    auto batch = commit_gemini({f, g, empty}, pk);
+    if (batch.size() != 3 || batch[0].xy != c.xy || batch[1].xy != commit_kzg(g, pk).xy || !batch[2].is_point_at_infinity()) {
+      printf("FAIL commit_gemini batch\n");
+      return 1;
+    }
+    // range-sharded commit inside one process: two ranks (own threads), exchange over peer memory
+    {
+      PublicKeyKZG r0(0), r1(0);
+      setup_kzg_range(r0, 0, 2, scalar_u64(123456789));
+      setup_kzg_range(r1, 2, 2, scalar_u64(123456789));
+      attach_peers({&r0, &r1});
+      Polynomial lo, hi;
+      lo.coef = {f.coef[0], f.coef[1]};
+      hi.coef = {f.coef[2], f.coef[3]};
+      CommitmentKZG c0, c1;
+      std::thread t0([&] { c0 = commit_kzg_sharded(lo, r0); });
+      std::thread t1([&] { c1 = commit_kzg_sharded(hi, r1); });
+      t0.join();
+      t1.join();
+      if (c0.xy != c.xy || c1.xy != c.xy) { printf("FAIL sharded commit\n"); return 1; }
+    }
     printf("OK\n");
   } catch (const std::exception& e) {
     printf("FAIL %s\n", e.what());

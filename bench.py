@@ -478,6 +478,14 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
     ex["quotient_scan_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                     "frac": (gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
                                     "note": "algorithmic 64 B/coefficient (read f, write q); the 3-kernel form moves 96 B"}
+    # the parallel scan spends ~2.5 Fr multiplies per coefficient (16-coefficient Horner runs twice + the
+    # Kogge-Stone steps), so the IMAD pipe, not HBM, is its nearer ceiling
+    _, imad = load_measured()
+    if imad and imad.get("imad_peak_Tops"):
+        timad = n * 2.5 * 264 / (ms_q * 1e-3) / 1e12
+        ex["quotient_scan_roofline_imad"] = {"bound": "int32_imad", "achieved": timad, "peak": imad["imad_peak_Tops"],
+                                             "unit": "TIMAD/s", "frac": timad / imad["imad_peak_Tops"],
+                                             "note": "2.5 Montgomery multiplies x 264 IMAD per coefficient"}
     del sc, q
     if log2n >= 20:
         n = 1 << 20

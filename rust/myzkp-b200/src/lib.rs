@@ -98,7 +98,45 @@ pub fn open_kzg(f: &Polynomial<FqOrder>, u: &FqOrder, pk: &GpuPublicKeyKZG) -> P
     ProofKZG { y: FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, &y)), w: point_from_bytes(&w) }
 }
 
-/// commit_gemini (gemini.rs:112-114)
+/// commit_gemini (gemini.rs:112-114): one batched call (small polynomials run concurrently on the GPU)
 pub fn commit_gemini(polys: &[Polynomial<FqOrder>], pk: &GpuPublicKeyKZG) -> Vec<CommitmentKZG> {
-    polys.iter().map(|p| commit_kzg(p, pk)).collect()
+    let bufs: Vec<Vec<u8>> = polys.iter().map(|p| marshal_scalars(&p.coef)).collect();
+    let ptrs: Vec<*const u8> = bufs.iter().map(|b| b.as_ptr()).collect();
+    let lens: Vec<usize> = polys.iter().map(|p| p.coef.len()).collect();
+    let mut out = vec![0u8; 64 * polys.len()];
+    check(pk.ctx, unsafe {
+        sys::myzkp_kzg_commit_batch(pk.ctx, ptrs.as_ptr(), lens.as_ptr(), polys.len(), out.as_mut_ptr())
+    });
+    out.chunks_exact(64).map(|c| point_from_bytes(c.try_into().unwrap())).collect()
+}
+
+/// Range-sharded prover, one `GpuPublicKeyKZG` per GPU: rank g holds powers_1[first, first + count).
+/// `alpha` is shared by the ranks (the reference draws it inside setup_kzg, kzg.rs:28).
+pub fn setup_kzg_range(device: i32, alpha: &FqOrder, first: usize, count: usize, g2: &G2Point) -> GpuPublicKeyKZG {
+    let mut ctx = ptr::null_mut();
+    let code = unsafe { sys::myzkp_ctx_create(&mut ctx, device) };
+    assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
+    let a = scalar_to_le(alpha);
+    check(ctx, unsafe { sys::myzkp_srs_generate_g1(ctx, a.as_ptr(), first, count) });
+    GpuPublicKeyKZG { ctx, powers_2: vec![g2.clone(), g2.mul_ref(alpha.get_value())] }
+}
+
+/// Map every rank's exchange buffer into every other rank (all ranks in this process).
+pub fn attach_peers(ranks: &[&GpuPublicKeyKZG]) {
+    let ctxs: Vec<*mut sys::myzkp_ctx> = ranks.iter().map(|r| r.ctx).collect();
+    for r in ranks {
+        check(r.ctx, unsafe { sys::myzkp_peer_export(r.ctx, ptr::null_mut()) });
+    }
+    for (g, r) in ranks.iter().enumerate() {
+        check(r.ctx, unsafe { sys::myzkp_peer_attach_local(r.ctx, g as i32, ranks.len() as i32, ctxs.as_ptr()) });
+    }
+}
+
+/// commit_kzg of the whole polynomial from this rank's coefficient slice; every rank returns the same point.
+/// Blocks until the peers have called it too: drive each rank from its own thread.
+pub fn commit_kzg_sharded(local_slice: &[FqOrder], pk: &GpuPublicKeyKZG) -> CommitmentKZG {
+    let bytes = marshal_scalars(local_slice);
+    let mut out = [0u8; 64];
+    check(pk.ctx, unsafe { sys::myzkp_kzg_commit_sharded(pk.ctx, bytes.as_ptr(), local_slice.len(), out.as_mut_ptr()) });
+    point_from_bytes(&out)
 }

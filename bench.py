@@ -501,6 +501,16 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
             ctx.gemini_fold_commit(coefs, rhos)
             best = min(best, (time.perf_counter() - t0) * 1e3)
         ex["gemini_2^20_fold_commit_21_polys_host_api_ms"] = best
+        # many small polynomials in one call (DAS rows: avail.rs:96 commits every row of the grid)
+        rows = [coefs[i * 1024:(i + 1) * 1024] for i in range(256)]
+        for _ in range(2):
+            ctx.commit_batch(rows)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ctx.commit_batch(rows)
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        ex["commit_batch_256_polys_of_2^10_host_api_ms"] = best
     return ex
 
 

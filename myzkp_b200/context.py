@@ -151,6 +151,18 @@ class Context:
         self._ck(self._lib.myzkp_kzg_commit(self.h, _ptr(a), a.shape[0], _ptr(out)))
         return point_from_bytes(out)
 
+    def commit_batch(self, polys):
+        """commit_gemini (gemini.rs:112-114): all polynomials in one call; the small ones share one MSM pipeline."""
+        arrs = [scalars_to_bytes(p) for p in polys]
+        k = len(arrs)
+        if k == 0:
+            return []
+        ptrs = (ctypes.c_void_p * k)(*[a.ctypes.data if a.shape[0] else None for a in arrs])
+        lens = (ctypes.c_size_t * k)(*[a.shape[0] for a in arrs])
+        out = np.zeros((k, 64), np.uint8)
+        self._ck(self._lib.myzkp_kzg_commit_batch(self.h, ptrs, lens, k, _ptr(out)))
+        return [point_from_bytes(out[i]) for i in range(k)]
+
     def open(self, coefs, u: int):
         a = scalars_to_bytes(coefs)
         ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()

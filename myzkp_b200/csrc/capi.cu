@@ -95,7 +95,7 @@ void free_ctx_scratch(myzkp_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                     &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
                     &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
-                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp};
+                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
   for (DevBuf* b : bufs) b->release();
 }
 
@@ -481,9 +481,65 @@ int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint
   return end_call_check_flag(ctx);
 }
 
+// Polynomials of at least this many coefficients get an MSM of their own (window tuned to their size);
+// everything smaller in a batch shares ONE pipeline (msm_batch_xyzz), so a batch of many small
+// polynomials costs its entries rather than one latency-bound pipeline each.
+constexpr size_t kBatchBelow = (size_t)1 << 19;
+constexpr size_t kBatchMaxPoints = (size_t)1 << 25;
+
 int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const size_t* ns, size_t k, uint8_t* out) {
   if (!ctx || (k && (!coefs || !ns || !out))) return MYZKP_ERR_INVALID_ARG;
-  for (size_t i = 0; i < k; i++) MZ_TRY(myzkp_kzg_commit(ctx, coefs[i], ns[i], out + 64 * i));
+  if (k == 0) return MYZKP_OK;
+  size_t total = 0;
+  for (size_t i = 0; i < k; i++) {
+    if (ns[i] && !coefs[i]) return MYZKP_ERR_INVALID_ARG;
+    if (ns[i] > ctx->srs_n) return fail(ctx, ns[i] && !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG,
+                                        "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+    total += ns[i];
+  }
+  MZ_TRY(begin_call(ctx));
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure((total ? total : 1) * 32));
+  MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure(k * (sizeof(XYZZ) + 64)));
+  XYZZ* res = ctx->xyzz_tmp.as<XYZZ>();  // results in processing order: small polynomials first, then the big ones
+  uint8_t* d_pts = reinterpret_cast<uint8_t*>(res + k);
+  std::vector<const uint32_t*> dptr(k);
+  {
+    uint32_t* p = ctx->scalars.as<uint32_t>();
+    for (size_t i = 0; i < k; i++) {
+      dptr[i] = p;
+      if (ns[i]) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(p, coefs[i], ns[i] * 32, cudaMemcpyHostToDevice, ctx->stream));
+      p += ns[i] * 8;
+    }
+  }
+  std::vector<size_t> order;  // order[j] = index of the polynomial whose result is res[j]
+  order.reserve(k);
+  std::vector<MsmItem> group;
+  size_t group_points = 0;
+  auto flush = [&]() -> int {
+    if (group.empty()) return MYZKP_OK;
+    int rc = msm_batch_xyzz(ctx, group.data(), group.size(), 0, res + (order.size() - group.size()));
+    group.clear();
+    group_points = 0;
+    return rc;
+  };
+  for (size_t i = 0; i < k; i++) {
+    if (ns[i] >= kBatchBelow) continue;
+    if (group.size() == 65535 || group_points + ns[i] > kBatchMaxPoints) MZ_TRY(flush());
+    group.push_back(MsmItem{dptr[i], ns[i]});
+    group_points += ns[i];
+    order.push_back(i);
+  }
+  MZ_TRY(flush());
+  for (size_t i = 0; i < k; i++) {
+    if (ns[i] < kBatchBelow) continue;
+    MZ_TRY(msm_xyzz(ctx, dptr[i], ns[i], 0, res + order.size()));
+    order.push_back(i);
+  }
+  MZ_TRY(xyzz_to_bytes(ctx, res, k, d_pts));
+  std::vector<uint8_t> host(k * 64);
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), d_pts, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_TRY(end_call_check_flag(ctx));
+  for (size_t j = 0; j < k; j++) memcpy(out + 64 * order[j], host.data() + 64 * j, 64);
   return MYZKP_OK;
 }
 
@@ -521,40 +577,45 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
       len /= 2;
     }
   }
-  // ... then one MSM per level.  Small levels are latency-bound, so they run concurrently on child
-  // contexts (own stream and scratch, same SRS table) while the large levels run on this stream.
-  const size_t small_below = (size_t)1 << 19;
+  // ... then the commitments.  Levels of >= 2^19 coefficients get their own MSM on this stream; all
+  // smaller levels (2^19 - 1 coefficients together) run as ONE batched pipeline on a child context
+  // (own stream and scratch, same SRS table), concurrently with the large ones.
   if (!ctx->fork_ev) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  int used_children = 0, next_child = 0;
+  std::vector<MsmItem> small_levels;
+  int first_small = m + 1;
   {
     uint32_t* cur = base;
     size_t len = n_pow2;
     for (int lvl = 0; lvl <= m; lvl++) {
-      if (len >= small_below) {
-        MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
-      } else {
-        myzkp_ctx* ch = nullptr;
-        MZ_TRY(get_child(ctx, next_child, &ch));
-        if (next_child >= used_children) {  // first use in this call: wait for the folds
-          MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, ctx->fork_ev, 0));
-          used_children = next_child + 1;
-        }
-        int rc = msm_xyzz(ch, cur, len, 0, res + lvl);
-        if (rc != MYZKP_OK) return fail(ctx, rc, ch->err.c_str());
-        ctx->launches += ch->launches;
-        ch->launches = 0;
-        next_child = (next_child + 1) % kMaxChildren;
+      if (len < kBatchBelow) {
+        if (small_levels.empty()) first_small = lvl;
+        small_levels.push_back(MsmItem{cur, len});
       }
       cur += len * 8;
       len /= 2;
     }
   }
-  for (int i = 0; i < used_children; i++) {
-    myzkp_ctx* ch = ctx->children[i];
+  myzkp_ctx* ch = nullptr;
+  if (!small_levels.empty()) {
+    MZ_TRY(get_child(ctx, 0, &ch));
+    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, ctx->fork_ev, 0));  // the folds come first
+    int rc = msm_batch_xyzz(ch, small_levels.data(), small_levels.size(), 0, res + first_small);
+    if (rc != MYZKP_OK) return fail(ctx, rc, ch->err.c_str());
+    ctx->launches += ch->launches;
+    ch->launches = 0;
     MZ_CUDA_TRY(ctx, cudaEventRecord(ch->join_ev, ch->stream));
-    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0));
   }
+  {
+    uint32_t* cur = base;
+    size_t len = n_pow2;
+    for (int lvl = 0; lvl < first_small; lvl++) {
+      MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
+      cur += len * 8;
+      len /= 2;
+    }
+  }
+  if (ch) MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0));
   MZ_TRY(xyzz_to_bytes(ctx, res, (size_t)(m + 1), d_pts));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pts, (size_t)(m + 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_folds && n_pow2 > 1)

@@ -91,6 +91,7 @@ struct myzkp_ctx {
   mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
+  mz::DevBuf descs;        // per-polynomial descriptors of a batched MSM
   mz::DevBuf xyzz_tmp;     // XYZZ temporaries (SRS generation)
   // host-API upload pipeline: chunks of a large polynomial are copied on copy_stream
   // while earlier chunks are already being committed on `stream`
@@ -159,7 +160,16 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 int msm_pick_window(const myzkp_ctx* ctx, size_t n);
 int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets);
 int msm_add_buckets(myzkp_ctx* ctx, XYZZ* a, const XYZZ* b, int c);
-int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out);
+int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, size_t K = 1);
+// K polynomials as ONE pipeline (shared sort / accumulate / merge, bucket range y per polynomial):
+// d_out[y] = sum_i items[y].d_scalars[i] * SRS[srs_off + i]
+struct MsmItem {
+  const uint32_t* d_scalars;
+  size_t n;
+};
+int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K);
+int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets);
+int msm_batch_xyzz(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, XYZZ* d_out);
 // XYZZ (device) -> canonical affine 64 B (device)
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
 int sum_partials(myzkp_ctx* ctx, const XYZZ* d_partials, size_t k, uint8_t* d_out64);

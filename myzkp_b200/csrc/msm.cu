@@ -17,6 +17,8 @@
 //                      partial to the bucket's owner.
 //   5. msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
 //                      running sums, then a tree sum.
+#include <vector>
+
 #include "ctx.cuh"
 
 namespace mz {
@@ -59,10 +61,26 @@ __device__ __forceinline__ XYZZ load_xyzz(const XYZZ* p) {
 // guarantees the top window absorbs the last carry for any scalar < 2^254.
 // key = |d| - 1 in [0, 2^(c-1)), or `sentinel` = 2^(c-1) for d == 0 (sorted to
 // the end and ignored).  val = sign << 31 | (row_of_bit[c w] * srs_n + srs_off + i).
-__global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ scalars, size_t n, int c, int W,
+// One launch recodes a batch of polynomials (blockIdx.y; a single MSM is a batch of one): polynomial
+// y has its own entry region [entry_off, entry_off + W n) and its own bucket range starting at
+// key_base; zero digits of every polynomial share the batch-wide sentinel key.
+struct RecodeDesc {
+  const uint32_t* scalars;
+  uint64_t n;
+  uint64_t entry_off;
+  uint32_t key_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const RecodeDesc* __restrict__ descs, int c, int W,
                                                   const uint8_t* __restrict__ row_of_bit, uint32_t srs_n,
-                                                  uint32_t srs_off, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ vals, int* __restrict__ flag) {
+                                                  uint32_t srs_off, uint32_t sentinel_key, uint32_t* __restrict__ keys_all,
+                                                  uint32_t* __restrict__ vals_all, int* __restrict__ flag) {
+  const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;  // a batch of one needs no descriptor upload
+  const uint32_t* __restrict__ scalars = dsc.scalars;
+  const size_t n = dsc.n;
+  uint32_t* __restrict__ keys = keys_all + dsc.entry_off;
+  uint32_t* __restrict__ vals = vals_all + dsc.entry_off;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr sc;
@@ -89,7 +107,7 @@ __global__ void __launch_bounds__(256) msm_recode(const uint32_t* __restrict__ s
     uint32_t neg = d > half ? 1u : 0u;
     uint32_t mag = neg ? ((1u << c) - d) : d;
     carry = neg;
-    uint32_t key = mag ? mag - 1 : half;
+    uint32_t key = mag ? dsc.key_base + mag - 1 : sentinel_key;
     uint32_t idx = (uint32_t)row_of_bit[bit] * srs_n + srs_off + (uint32_t)i;
     keys[(size_t)w * n + i] = key;
     vals[(size_t)w * n + i] = idx | (neg << 31);
@@ -192,8 +210,11 @@ __global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ bucket
 // ---------------------------------------------------------------------------
 // thread j owns buckets [j*Lb, (j+1)*Lb): running sums give A = sum B and
 // S = sum (idx - j*Lb + 1) B; its contribution is S + (j*Lb) * A.
-__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ buckets, uint32_t nb, uint32_t Lb,
-                                                         XYZZ* __restrict__ out) {
+// blockIdx.y = bucket set of a batch (sets of nb buckets back to back; out: nchunks partials per set)
+__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ buckets_all, uint32_t nb, uint32_t Lb,
+                                                         XYZZ* __restrict__ out_all, uint32_t nchunks) {
+  const XYZZ* __restrict__ buckets = buckets_all + (size_t)blockIdx.y * nb;
+  XYZZ* __restrict__ out = out_all + (size_t)blockIdx.y * nchunks;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t lo = (uint64_t)j * Lb;
   if (lo >= nb) return;
@@ -219,9 +240,13 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict_
 
 // block-wide tree sum of XYZZ values; out[blockIdx.x] = sum of in[block range]
 constexpr int kTreeThreads = 128;
-__global__ void __launch_bounds__(kTreeThreads) xyzz_tree_reduce(const XYZZ* __restrict__ in, uint64_t n,
-                                                                 XYZZ* __restrict__ out) {
+// blockIdx.y = independent segment (in: in_stride values apart, out: out_stride)
+__global__ void __launch_bounds__(kTreeThreads) xyzz_tree_reduce(const XYZZ* __restrict__ in_all, uint64_t n,
+                                                                 XYZZ* __restrict__ out_all, uint64_t in_stride,
+                                                                 uint64_t out_stride) {
   __shared__ XYZZ sm[kTreeThreads];
+  const XYZZ* __restrict__ in = in_all + (size_t)blockIdx.y * in_stride;
+  XYZZ* __restrict__ out = out_all + (size_t)blockIdx.y * out_stride;
   uint64_t i = (uint64_t)blockIdx.x * (2 * kTreeThreads) + threadIdx.x;
   XYZZ acc = xyzz_inf();
   if (i < n) acc = load_xyzz(in + i);
@@ -278,11 +303,12 @@ static int pick_window(const myzkp_ctx* ctx, size_t n) {
 
 // tree-sum `count` XYZZ values living in buffer `a` (ping-pong with `b`); the
 // single result ends in *d_out
-static int tree_sum(myzkp_ctx* ctx, XYZZ* a, XYZZ* b, uint64_t count, XYZZ* d_out) {
+// K independent segments of `count` values each (segment y starts at a + y * count); results in d_out[y]
+static int tree_sum(myzkp_ctx* ctx, XYZZ* a, XYZZ* b, uint64_t count, XYZZ* d_out, uint32_t K = 1) {
   while (true) {
     uint64_t blocks = (count + 2 * kTreeThreads - 1) / (2 * kTreeThreads);
     XYZZ* dst = (blocks == 1) ? d_out : b;
-    xyzz_tree_reduce<<<(unsigned)blocks, kTreeThreads, 0, ctx->stream>>>(a, count, dst);
+    xyzz_tree_reduce<<<dim3((unsigned)blocks, K), kTreeThreads, 0, ctx->stream>>>(a, count, dst, count, blocks);
     MZ_LAUNCH_CHECK(ctx);
     if (blocks == 1) return MYZKP_OK;
     count = blocks;
@@ -321,16 +347,68 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   return msm_reduce_buckets(ctx, c, ctx->buckets.as<XYZZ>(), d_out);
 }
 
+// Window for a batch of K polynomials run as one pipeline: latency does not matter there, so take
+// the supported window with the least work - 10 multiplies per entry (W(c) entries per coefficient)
+// against 2 x 14 multiplies per bucket (2^(c-1) buckets per polynomial) - within a 2 GiB bucket budget.
+int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K) {
+  uint64_t total = 0;
+  for (size_t y = 0; y < K; y++) total += items[y].n;
+  int best = 0;
+  double best_cost = 0;
+  for (int c = 4; c <= 22; c++) {
+    if (!((ctx->windows >> c) & 1)) continue;
+    const uint64_t nbk = (uint64_t)K << (c - 1);
+    if (nbk * sizeof(XYZZ) > (2ull << 30) || nbk >= (1ull << 32) - 1) continue;
+    const int W = (255 + c - 1) / c;
+    const double cost = 10.0 * W * (double)total + 28.0 * (double)nbk;
+    if (!best || cost < best_cost) { best = c; best_cost = cost; }
+  }
+  return best;
+}
+
+// K commitments in one pipeline: d_out[y] = sum_i items[y].scalars[i] * SRS[srs_off + i]
+int msm_batch_xyzz(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, XYZZ* d_out) {
+  if (K == 0) return MYZKP_OK;
+  if (K == 1) return msm_xyzz(ctx, items[0].d_scalars, items[0].n, srs_off, d_out);
+  const int c = msm_pick_window_batch(ctx, items, K);
+  if (!c) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch too large for one pipeline");
+  MZ_CUDA_TRY(ctx, ctx->buckets.ensure(((size_t)K << (c - 1)) * sizeof(XYZZ)));
+  MZ_TRY(msm_fill_buckets_batch(ctx, items, K, srs_off, c, ctx->buckets.as<XYZZ>()));
+  return msm_reduce_buckets(ctx, c, ctx->buckets.as<XYZZ>(), d_out, K);
+}
+
 // steps 1-4: recode, sort, accumulate, merge -> `buckets` (2^(c-1) XYZZ, overwritten) holds the
 // bucket sums of sum_i scalars[i] * SRS[srs_off + i] for window c
 int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets) {
+  MsmItem one{d_scalars, n};
+  return msm_fill_buckets_batch(ctx, &one, 1, srs_off, c, buckets);
+}
+
+// The same for a batch of K polynomials sharing the window c (each against SRS[srs_off ...]) in ONE
+// pipeline: polynomial y owns the bucket range [y nb, (y+1) nb) of `buckets` (K 2^(c-1) XYZZ), so one
+// sort, one accumulate and one merge serve the whole batch - many small commitments cost their
+// entries, not K latency-bound pipelines.
+int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets) {
   if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
-  if (srs_off + n > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
   if (c < 1 || c > 24 || !((ctx->windows >> c) & 1)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
+  if (K == 0 || K > 65535) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch of 1..65535 polynomials");
   const int W = (255 + c - 1) / c;
-  const uint32_t nb = 1u << (c - 1);
-  const uint64_t M = (uint64_t)W * n;
+  const uint32_t nb1 = 1u << (c - 1);
+  if ((uint64_t)K * nb1 >= (1ull << 32) - 1) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch needs more than 2^32 buckets");
+  const uint32_t nb = (uint32_t)K * nb1;  // buckets of the whole batch; also the sentinel key
+  uint64_t M = 0;
+  size_t n = 0;  // longest polynomial
+  std::vector<RecodeDesc> descs(K);
+  for (size_t y = 0; y < K; y++) {
+    if (srs_off + items[y].n > ctx->srs_n)
+      return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+    descs[y] = RecodeDesc{items[y].d_scalars, items[y].n, M, (uint32_t)y * nb1, 0};
+    M += (uint64_t)W * items[y].n;
+    if (items[y].n > n) n = items[y].n;
+  }
   if (M >= (1ull << 32)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "MSM too large for 32-bit entry indices");
+  int sort_bits = c;  // c-1 bucket bits + the sentinel bit
+  while (sort_bits < 32 && (1ull << sort_bits) <= nb) sort_bits++;
 
   MZ_CUDA_TRY(ctx, ctx->keys_a.ensure(M * 4));
   MZ_CUDA_TRY(ctx, ctx->keys_b.ensure(M * 4));
@@ -350,15 +428,23 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
   ctx->phase_valid[slot] = false;
   MZ_PHASE(0);
   // 1. recode
-  msm_recode<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, n, c, W, ctx->d_row_of_bit,
-                                                                   (uint32_t)ctx->srs_n, (uint32_t)srs_off, keys_a,
-                                                                   vals_a, flag);
-  MZ_LAUNCH_CHECK(ctx);
+  const RecodeDesc* d_descs = nullptr;
+  if (K > 1) {
+    MZ_CUDA_TRY(ctx, ctx->descs.ensure(K * sizeof(RecodeDesc)));
+    // pageable source: staged before the call returns
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->descs.p, descs.data(), K * sizeof(RecodeDesc), cudaMemcpyHostToDevice, ctx->stream));
+    d_descs = ctx->descs.as<RecodeDesc>();
+  }
+  if (n) {
+    msm_recode<<<dim3((unsigned)((n + 255) / 256), (unsigned)K), 256, 0, ctx->stream>>>(
+        descs[0], d_descs, c, W, ctx->d_row_of_bit, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb, keys_a, vals_a, flag);
+    MZ_LAUNCH_CHECK(ctx);
+  }
 
   MZ_PHASE(1);
   // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit)
   uint32_t *keys_s = nullptr, *vals_s = nullptr;
-  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, c, &keys_s, &vals_s));
+  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, sort_bits, &keys_s, &vals_s));
 
   // 3. accumulate
   // Segment length: enough segments to fill the GPU several times over, but not much
@@ -381,6 +467,11 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
       uint64_t l2 = (M + waves * wave - 1) / (waves * wave);
       if (l2 >= 8 && l2 <= 256) L = (uint32_t)l2;
     }
+  }
+  if (M == 0) {  // nothing but empty polynomials: every bucket is the point at infinity
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+    ctx->phase_pending = false;
+    return MYZKP_OK;
   }
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
@@ -438,20 +529,22 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
   return MYZKP_OK;
 }
 
-// step 5: sum_k (k+1) * buckets[k] -> *d_out (XYZZ)
-int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out) {
+// step 5: sum_k (k+1) * buckets[k] -> *d_out (XYZZ); K bucket sets back to back -> d_out[0..K)
+int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, size_t K) {
   const uint32_t nb = 1u << (c - 1);
   const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
   const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
   // chunk length: about one wave of (3 blocks x 128 threads) per SM
   uint32_t Lb = 8;
-  while (Lb < 64 && (uint64_t)nb / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
+  while (Lb < 64 && (uint64_t)nb * K / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
+  if (Lb > nb) Lb = nb;
   uint32_t nchunks = (nb + Lb - 1) / Lb;
-  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)nchunks * sizeof(XYZZ)));
-  MZ_CUDA_TRY(ctx, ctx->red_b.ensure(((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
-  msm_bucket_reduce<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(buckets, nb, Lb, ctx->red_a.as<XYZZ>());
+  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)K * nchunks * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->red_b.ensure((size_t)K * ((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
+  msm_bucket_reduce<<<dim3((nchunks + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(buckets, nb, Lb,
+                                                                                      ctx->red_a.as<XYZZ>(), nchunks);
   MZ_LAUNCH_CHECK(ctx);
-  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out));
+  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out, (uint32_t)K));
   if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][5], ctx->stream));
   ctx->phase_valid[slot] = timing;
   ctx->phase_pending = false;

@@ -40,8 +40,8 @@ def split_and_fold_commit(coef, rhos: Sequence[int], pk: PublicKeyKZG, want_fold
 
 
 def commit_gemini(polys: Sequence[Polynomial], pk: PublicKeyKZG) -> List[G1Point]:
-    """gemini.rs:112-114: one commit_kzg per polynomial."""
-    return [G1Point._from_tuple(pk.ctx.commit(p._wire())) for p in polys]
+    """gemini.rs:112-114: a commit_kzg per polynomial - here one batched call (myzkp_kzg_commit_batch)."""
+    return [G1Point._from_tuple(t) for t in pk.ctx.commit_batch([p._wire() for p in polys])]
 
 
 class ProofGemini:

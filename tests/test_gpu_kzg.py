@@ -322,6 +322,58 @@ def test_peer_exchange_timeout_is_reported(ctx):
         a.close(); b.close()
 
 
+def test_commit_batch_one_pipeline(ctx):
+    """myzkp_kzg_commit_batch: many small polynomials (DAS rows, Gemini levels) share one MSM pipeline
+    (bucket range per polynomial); empty, constant, zero and max-length polynomials included."""
+    rnd = random.Random(77)
+    alpha = 0x5DEECE66D1234567
+    nmax = 700
+    ctx.srs_generate(alpha, nmax)
+    sizes = [0, 1, 2, nmax, 3, 64, 65, 256] + [rnd.randrange(0, nmax + 1) for _ in range(150)]
+    polys = []
+    for j, n in enumerate(sizes):
+        kind = j % 5
+        if kind == 0:
+            ints = [rnd.randrange(R) for _ in range(n)]
+        elif kind == 1:
+            ints = [rnd.randrange(256) for _ in range(n)]  # byte-valued, as the DAS callers produce
+        elif kind == 2:
+            ints = [rnd.choice([0, 0, 1, R - 1, R - 2]) for _ in range(n)]
+        elif kind == 3:
+            ints = [0] * n
+        else:
+            ints = [rnd.randrange(R) if rnd.random() < 0.3 else 0 for _ in range(n)]
+        polys.append(ints)
+    got = ctx.commit_batch(polys)
+    assert len(got) == len(polys)
+    for ints, g in zip(polys, got):
+        assert g == o.expected_commit(ints, alpha)
+    # batches of one and of none
+    assert ctx.commit_batch([polys[3]]) == [o.expected_commit(polys[3], alpha)]
+    assert ctx.commit_batch([]) == []
+    # a polynomial longer than the SRS is rejected for the whole batch
+    with pytest.raises(mz.MyzkpError):
+        ctx.commit_batch([polys[0], [1] * (nmax + 1)])
+    # non-canonical scalar anywhere in the batch
+    bad = np.zeros((3, 32), np.uint8)
+    bad[1] = np.frombuffer(R.to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(mz.MyzkpError):
+        ctx.commit_batch([polys[5], bad])
+
+
+def test_commit_batch_mixed_large_and_small(ctx):
+    """A batch with one polynomial above the own-MSM threshold (2^19) next to small ones: results come
+    back in caller order."""
+    alpha = 0x1F2E3D4C5B6A7988
+    n_big = (1 << 19) + 5
+    ctx.srs_generate(alpha, n_big)
+    big = synth.random_scalars(n_big, 991)
+    small = [synth.random_scalars(n, 992 + n) for n in (1000, 17, 40000)]
+    got = ctx.commit_batch([small[0], big, small[1], small[2]])
+    exp = [o.expected_commit(synth.limbs_to_ints(a), alpha) for a in (small[0], big, small[1], small[2])]
+    assert got == exp
+
+
 def test_chunked_upload_pipeline(ctx):
     """Host-buffer commit/open split into upload chunks (auto from 2^23) - forced here at a small size."""
     n = 5003

@@ -94,7 +94,10 @@ int myzkp_kzg_commit(myzkp_ctx* ctx, const uint8_t* coefs_le /* n*32 */, size_t 
  * n <= 1 -> W = infinity, y = f_0 (or 0) (polynomial.rs:372-374). */
 int myzkp_kzg_open(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32],
                    uint8_t out_y[32], uint8_t out_w[64]);
-/* commit_gemini (gemini.rs:112-114) over k polynomials. */
+/* commit_gemini (gemini.rs:112-114) over k polynomials: out = k x 64 B in caller order.  Polynomials below
+ * 2^19 coefficients share ONE MSM pipeline (a bucket range per polynomial), so many small commitments -
+ * Gemini's folds, the rows of a DAS grid (das/avail.rs:96) - cost their entries rather than one
+ * latency-bound pipeline each; larger ones get an MSM of their own.  Any error rejects the whole batch. */
 int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const size_t* ns, size_t k,
                            uint8_t* out /* k*64 */);
 /* split_and_fold (gemini.rs:51-103) + commit_gemini: n_pow2 = 2^m coefficients,

@@ -504,12 +504,27 @@ int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const si
   uint8_t* d_pts = reinterpret_cast<uint8_t*>(res + k);
   std::vector<const uint32_t*> dptr(k);
   {
+    // polynomials land back to back on the device; runs that are already back to back on the host
+    // (rows of one matrix) travel as one copy
     uint32_t* p = ctx->scalars.as<uint32_t>();
+    const uint8_t* run_src = nullptr;
+    uint32_t* run_dst = p;
+    size_t run_bytes = 0;
     for (size_t i = 0; i < k; i++) {
       dptr[i] = p;
-      if (ns[i]) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(p, coefs[i], ns[i] * 32, cudaMemcpyHostToDevice, ctx->stream));
+      if (ns[i]) {
+        if (run_bytes && coefs[i] == run_src + run_bytes) {
+          run_bytes += ns[i] * 32;
+        } else {
+          if (run_bytes) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, ctx->stream));
+          run_src = coefs[i];
+          run_dst = p;
+          run_bytes = ns[i] * 32;
+        }
+      }
       p += ns[i] * 8;
     }
+    if (run_bytes) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   std::vector<size_t> order;  // order[j] = index of the polynomial whose result is res[j]
   order.reserve(k);

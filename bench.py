@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_IMAD_PER_POINT = 42240  # 16 windows x (8M+2S) x 264 IMAD (c = 16 canonical)
-IMAD_PER_MADD = 8 * 264 + 2 * 208  # 8 Montgomery multiplies (264 IMAD) + 2 dedicated squarings ((36 + 64) * 2 + 8)
+IMAD_PER_MADD = 6 * 264 + 392 + 2 * 208  # 6 Montgomery multiplies (264 IMAD), one sum of two products with a single
+# reduction (fe_mul2: 3 x 64 wide products x 2 + 8) and 2 dedicated squarings ((36 + 64) * 2 + 8)
 SORT_BYTES_PER_POINT = 672  # recode + sort phases
 
 
@@ -367,7 +368,7 @@ def main():
             "executed_TIMAD_s": executed, "executed_frac": (executed / imad_peak) if imad_peak else None,
             "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step,
             "note": "achieved = points x 42240 algorithmic IMAD (SURVEY 8d, c=16 XYZZ) / accumulate time; executed = "
-                    "entries x %d IMAD actually issued (8M at 264 + 2S at 208; window c=%d, %d windows)" % (IMAD_PER_MADD, info.get("window_bits", 0), info.get("windows", 0)),
+                    "entries x %d IMAD actually issued (6M at 264 + one two-product multiply at 392 + 2S at 208; window c=%d, %d windows)" % (IMAD_PER_MADD, info.get("window_bits", 0), info.get("windows", 0)),
         }
         if sort_ms > 0 and peaks.get("hbm_gbs"):
             gbs = n_local * SORT_BYTES_PER_POINT / (sort_ms * 1e-3) / 1e9

@@ -308,6 +308,61 @@ MZ_HD Fe<PR> fe_mul(const Fe<PR>& a, const Fe<PR>& b) {
   return r;
 }
 
+// --- sum of two products with ONE reduction -----------------------------------
+// (a*b + c*d) R^-1 mod m: every row adds a*b_i, c*d_i and m*modulus to the same accumulators,
+// so the pair costs 192 wide multiplies instead of 2 x 128.  Bounds (inputs < modulus < 2^254):
+// the running sum after a row's shift is < 3 * 2^254 (1 + 2^-32) < 2^256 and before it
+// < 2^288, which is what the (E, O) arrays hold; the final value is
+// < (2 m^2 + 2^256 m) / 2^256 < 1.38 m, so one conditional subtraction suffices.
+namespace detail {
+template <class PR>
+MZ_HD void mont_row2(uint32_t* E, uint32_t* O, const ArrAcc& a, uint32_t bi, const ArrAcc& c, uint32_t di,
+                     bool first) {
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      mul_wide(a(j + 1), bi, O[j], O[j + 1]);
+      mul_wide(a(j), bi, E[j], E[j + 1]);
+    }
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+    row_shift_mad_odd(O, a, bi);
+    row_mad_even(E, a, bi);
+    O[7] = addc(O[7], 0);
+  }
+  row_mad_odd(O, c, di);  // the total stays < 2^288: no carry out of column 8
+  row_mad_even(E, c, di);
+  O[7] = addc(O[7], 0);
+  uint32_t m = mul_lo(E[0], PR::INV);
+  row_mad_odd(O, ModAcc<PR>(), m);
+  row_mad_even(E, ModAcc<PR>(), m);
+  O[7] = addc(O[7], 0);
+}
+}  // namespace detail
+
+template <class PR>
+MZ_HD Fe<PR> fe_mul2(const Fe<PR>& a, const Fe<PR>& b, const Fe<PR>& c, const Fe<PR>& d) {
+  uint32_t E[8], O[8];
+  detail::ArrAcc aa{a.v}, cc{c.v};
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    detail::mont_row2<PR>(E, O, aa, b.v[i], cc, d.v[i], i == 0);
+    detail::mont_row2<PR>(O, E, aa, b.v[i + 1], cc, d.v[i + 1], false);
+  }
+  Fe<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  fe_reduce_once(r);
+  return r;
+}
+// a*b - c*d
+template <class PR>
+MZ_HD Fe<PR> fe_mul_sub_mul(const Fe<PR>& a, const Fe<PR>& b, const Fe<PR>& c, const Fe<PR>& d) {
+  return fe_mul2(a, b, fe_neg(c), d);
+}
+
 // --- Montgomery square --------------------------------------------------------
 // a^2 costs 36 wide products instead of 64: the 28 products a_i*a_j (i < j) are summed once
 // and doubled, the 8 squares a_i^2 are added on top.  The 512-bit result S is then reduced

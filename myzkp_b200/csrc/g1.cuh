@@ -56,7 +56,7 @@ MZ_HD XYZZ xyzz_mdbl(const Affine& p) {
   Fq xx = fe_sqr(p.x);
   Fq m = fe_add(fe_dbl(xx), xx);
   r.x = fe_sub(fe_sqr(m), fe_dbl(s));
-  r.y = fe_sub(fe_mul(m, fe_sub(s, r.x)), fe_mul(w, p.y));
+  r.y = fe_mul_sub_mul(m, fe_sub(s, r.x), w, p.y);  // one reduction for both products
   r.zz = v;
   r.zzz = w;
   return r;
@@ -72,7 +72,7 @@ MZ_HD void xyzz_dbl(XYZZ& p) {
   Fq xx = fe_sqr(p.x);
   Fq m = fe_add(fe_dbl(xx), xx);
   Fq x3 = fe_sub(fe_sqr(m), fe_dbl(s));
-  Fq y3 = fe_sub(fe_mul(m, fe_sub(s, x3)), fe_mul(w, p.y));
+  Fq y3 = fe_mul_sub_mul(m, fe_sub(s, x3), w, p.y);
   p.x = x3;
   p.y = y3;
   p.zz = fe_mul(v, p.zz);
@@ -97,7 +97,7 @@ MZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
   Fq ppp = fe_mul(p, pp);
   Fq qq = fe_mul(acc.x, pp);
   Fq x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fq y3 = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(acc.y, ppp));
+  Fq y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), acc.y, ppp);  // one reduction for both products
   acc.x = x3;
   acc.y = y3;
   acc.zz = fe_mul(acc.zz, pp);
@@ -123,7 +123,7 @@ MZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
   Fq ppp = fe_mul(p, pp);
   Fq qq = fe_mul(u1, pp);
   Fq x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fq y3 = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(s1, ppp));
+  Fq y3 = fe_mul_sub_mul(r, fe_sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fe_mul(fe_mul(acc.zz, q.zz), pp);

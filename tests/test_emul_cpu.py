@@ -68,6 +68,18 @@ def test_field_ops(name, m):
     for _ in range(3000):
         x = sum(rnd.choice(limbs) << (32 * i) for i in range(8)) % m if rnd.random() < 0.5 else rnd.randrange(m)
         assert u1("sqr", x) == x * x * rinv % m
+    # sum of two products with one reduction (bounds: all-maximal operands, carry-heavy limbs)
+    def q4(fn, x, y, z, w):
+        out = A8()
+        getattr(L, f"emul_{name}_{fn}")(tl(x), tl(y), tl(z), tl(w), out)
+        return fl(out)
+
+    assert q4("mul2", m - 1, m - 1, m - 1, m - 1) == 2 * (m - 1) * (m - 1) * rinv % m
+    for _ in range(4000):
+        x, y, z, w = [(sum(rnd.choice(limbs) << (32 * i) for i in range(8)) % m if rnd.random() < 0.4
+                       else rnd.choice(edge) if rnd.random() < 0.2 else rnd.randrange(m)) for _ in range(4)]
+        assert q4("mul2", x, y, z, w) == (x * y + z * w) * rinv % m
+        assert q4("mul_sub_mul", x, y, z, w) == (x * y - z * w) * rinv % m
     for x in vals[:24]:
         exp = (pow(x, -1, m) if x else 0) * RR % m
         assert u1("inv", x * RR % m) == exp

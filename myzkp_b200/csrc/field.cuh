@@ -390,6 +390,147 @@ MZ_HD void redc_row(uint32_t* E, uint32_t* O) {
 }
 }  // namespace detail
 
+// Montgomery reduction of a 16-limb value S < 2^256 * modulus: 8 rows of m * modulus on the low half,
+// then the high half is added (result < modulus + S / 2^256 < 2 * modulus) and reduced once.
+namespace detail {
+template <class PR>
+MZ_HD Fe<PR> redc_wide(const uint32_t* S) {
+  uint32_t E[8], O[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { E[i] = S[i]; O[i] = 0; }
+  {
+    uint32_t m = mul_lo(E[0], PR::INV);
+    row_mad_odd(O, ModAcc<PR>(), m);
+    row_mad_even(E, ModAcc<PR>(), m);
+    O[7] = addc(O[7], 0);
+  }
+  redc_row<PR>(O, E);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    redc_row<PR>(E, O);
+    redc_row<PR>(O, E);
+  }
+  Fe<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  r.v[0] = add_cc(r.v[0], S[8]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], S[8 + i]);
+  r.v[7] = addc(r.v[7], S[15]);
+  fe_reduce_once(r);
+  return r;
+}
+
+// 4 x 4 limb product (16 wide multiplies).  P[k] = column k, Q[k] = column k + 1: a product whose low
+// column is even goes to P, odd to Q, so every row is one carry chain per accumulator.  A chain that
+// ends on a column an earlier row wrote may carry out into the next (still untouched) column; a chain
+// that ends on an untouched column adds hi(product) <= 2^32 - 2 to a carry bit and cannot carry out.
+MZ_HD void mul4(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  uint32_t P[8], Q[7];
+  // row 0
+  mul_wide(a[0], b[0], P[0], P[1]);
+  mul_wide(a[2], b[0], P[2], P[3]);
+  mul_wide(a[1], b[0], Q[0], Q[1]);
+  mul_wide(a[3], b[0], Q[2], Q[3]);
+  // row 1: a0,a2 -> columns 1,3 (Q0..Q3, all written -> carry to Q4); a1,a3 -> columns 2,4 (P2,P3 written; P4,P5 new)
+  Q[0] = mad_lo_cc(a[0], b[1], Q[0]);  Q[1] = madc_hi_cc(a[0], b[1], Q[1]);
+  Q[2] = madc_lo_cc(a[2], b[1], Q[2]); Q[3] = madc_hi_cc(a[2], b[1], Q[3]);
+  Q[4] = addc(0, 0);
+  P[2] = mad_lo_cc(a[1], b[1], P[2]);  P[3] = madc_hi_cc(a[1], b[1], P[3]);
+  P[4] = madc_lo_cc(a[3], b[1], 0);    P[5] = madc_hi(a[3], b[1], 0);
+  // row 2: a0,a2 -> columns 2,4 (P2..P5 written -> carry to P6); a1,a3 -> columns 3,5 (Q2,Q3 written, Q4 carry bit, Q5 new)
+  P[2] = mad_lo_cc(a[0], b[2], P[2]);  P[3] = madc_hi_cc(a[0], b[2], P[3]);
+  P[4] = madc_lo_cc(a[2], b[2], P[4]); P[5] = madc_hi_cc(a[2], b[2], P[5]);
+  P[6] = addc(0, 0);
+  Q[2] = mad_lo_cc(a[1], b[2], Q[2]);  Q[3] = madc_hi_cc(a[1], b[2], Q[3]);
+  Q[4] = madc_lo_cc(a[3], b[2], Q[4]); Q[5] = madc_hi(a[3], b[2], 0);
+  // row 3: a0,a2 -> columns 3,5 (Q2..Q5 written -> carry to Q6); a1,a3 -> columns 4,6 (P4,P5 written, P6 carry bit, P7 new)
+  Q[2] = mad_lo_cc(a[0], b[3], Q[2]);  Q[3] = madc_hi_cc(a[0], b[3], Q[3]);
+  Q[4] = madc_lo_cc(a[2], b[3], Q[4]); Q[5] = madc_hi_cc(a[2], b[3], Q[5]);
+  Q[6] = addc(0, 0);
+  P[4] = mad_lo_cc(a[1], b[3], P[4]);  P[5] = madc_hi_cc(a[1], b[3], P[5]);
+  P[6] = madc_lo_cc(a[3], b[3], P[6]); P[7] = madc_hi(a[3], b[3], 0);
+  // r = P + Q * 2^32 (< 2^256)
+  r[0] = P[0];
+  r[1] = add_cc(P[1], Q[0]);
+#pragma unroll
+  for (int k = 2; k < 7; k++) r[k] = addc_cc(P[k], Q[k - 1]);
+  r[7] = addc(P[7], Q[6]);
+}
+
+// d = |x - y| over 4 limbs; returns all-ones if x < y
+MZ_HD uint32_t absdiff4(const uint32_t* x, const uint32_t* y, uint32_t* d) {
+  d[0] = sub_cc(x[0], y[0]);
+  d[1] = subc_cc(x[1], y[1]);
+  d[2] = subc_cc(x[2], y[2]);
+  d[3] = subc_cc(x[3], y[3]);
+  const uint32_t neg = subc(0, 0);  // all-ones on borrow
+  d[0] = sub_cc(d[0] ^ neg, neg);
+  d[1] = subc_cc(d[1] ^ neg, neg);
+  d[2] = subc_cc(d[2] ^ neg, neg);
+  d[3] = subc(d[3] ^ neg, neg);
+  return neg;
+}
+
+// S (16 limbs) = a * b by one level of subtractive Karatsuba: 3 x 16 wide multiplies instead of 64.
+// a = a0 + a1 2^128, b = b0 + b1 2^128:  a0 b1 + a1 b0 = a0 b0 + a1 b1 + (a0 - a1)(b1 - b0).
+// The additions run on the integer-add pipe, which the multiply-bound kernels leave idle.
+MZ_HD void mul8_karatsuba(const uint32_t* a, const uint32_t* b, uint32_t* S) {
+  uint32_t z0[8], z2[8], zm[8], da[4], db[4];
+  mul4(a, b, z0);
+  mul4(a + 4, b + 4, z2);
+  const uint32_t neg = absdiff4(a, a + 4, da) ^ absdiff4(b + 4, b, db);  // sign of (a0 - a1)(b1 - b0)
+  mul4(da, db, zm);
+  // mid = z0 + z2 +- zm as a 9-limb two's-complement value (true value in [0, 2^257))
+  uint32_t mid[9];
+  mid[0] = add_cc(z0[0], z2[0]);
+#pragma unroll
+  for (int k = 1; k < 8; k++) mid[k] = addc_cc(z0[k], z2[k]);
+  mid[8] = addc(0, 0);
+  (void)add_cc(neg, neg);  // CF = 1 when subtracting: -zm = ~zm + 1
+#pragma unroll
+  for (int k = 0; k < 8; k++) mid[k] = addc_cc(mid[k], zm[k] ^ neg);
+  mid[8] = addc(mid[8], neg);
+  // S = z0 + mid 2^128 + z2 2^256
+#pragma unroll
+  for (int k = 0; k < 4; k++) S[k] = z0[k];
+  S[4] = add_cc(z0[4], mid[0]);
+  S[5] = addc_cc(z0[5], mid[1]);
+  S[6] = addc_cc(z0[6], mid[2]);
+  S[7] = addc_cc(z0[7], mid[3]);
+  S[8] = addc_cc(z2[0], mid[4]);
+  S[9] = addc_cc(z2[1], mid[5]);
+  S[10] = addc_cc(z2[2], mid[6]);
+  S[11] = addc_cc(z2[3], mid[7]);
+  S[12] = addc_cc(z2[4], mid[8]);
+  S[13] = addc_cc(z2[5], 0);
+  S[14] = addc_cc(z2[6], 0);
+  S[15] = addc(z2[7], 0);
+}
+}  // namespace detail
+
+// Karatsuba variants of the multiply: 48 + 64 wide multiplies (fe_mul: 120 + 8 high halves),
+// 96 + 64 for the two-product form (192).
+template <class PR>
+MZ_HD Fe<PR> fe_mul_k(const Fe<PR>& a, const Fe<PR>& b) {
+  uint32_t S[16];
+  detail::mul8_karatsuba(a.v, b.v, S);
+  return detail::redc_wide<PR>(S);
+}
+template <class PR>
+MZ_HD Fe<PR> fe_mul2_k(const Fe<PR>& a, const Fe<PR>& b, const Fe<PR>& c, const Fe<PR>& d) {
+  uint32_t S[16], T[16];
+  detail::mul8_karatsuba(a.v, b.v, S);
+  detail::mul8_karatsuba(c.v, d.v, T);
+  S[0] = add_cc(S[0], T[0]);
+#pragma unroll
+  for (int k = 1; k < 15; k++) S[k] = addc_cc(S[k], T[k]);
+  S[15] = addc(S[15], T[15]);  // a b + c d < 2^509
+  return detail::redc_wide<PR>(S);
+}
+
 template <class PR>
 MZ_HD Fe<PR> fe_sqr(const Fe<PR>& a) {
   const uint32_t* v = a.v;
@@ -458,34 +599,7 @@ MZ_HD Fe<PR> fe_sqr(const Fe<PR>& a) {
     S[2 * i] = madc_lo_cc(v[i], v[i], detail::shl1(T[2 * i - 1], T[2 * i]));
     S[2 * i + 1] = madc_hi_cc(v[i], v[i], detail::shl1(T[2 * i], T[2 * i + 1]));
   }
-  // Montgomery reduction of the low half
-  uint32_t E[8], O[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) { E[i] = S[i]; O[i] = 0; }
-  {
-    uint32_t m = mul_lo(E[0], PR::INV);
-    detail::row_mad_odd(O, detail::ModAcc<PR>(), m);
-    detail::row_mad_even(E, detail::ModAcc<PR>(), m);
-    O[7] = addc(O[7], 0);
-  }
-  detail::redc_row<PR>(O, E);
-#pragma unroll
-  for (int i = 2; i < 8; i += 2) {
-    detail::redc_row<PR>(E, O);
-    detail::redc_row<PR>(O, E);
-  }
-  Fe<PR> r;
-  r.v[0] = add_cc(E[0], O[1]);
-#pragma unroll
-  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
-  r.v[7] = addc(E[7], 0);
-  // + high half of S (r < modulus + 2^252 < 2 * modulus)
-  r.v[0] = add_cc(r.v[0], S[8]);
-#pragma unroll
-  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], S[8 + i]);
-  r.v[7] = addc(r.v[7], S[15]);
-  fe_reduce_once(r);
-  return r;
+  return detail::redc_wide<PR>(S);
 }
 
 template <class PR>

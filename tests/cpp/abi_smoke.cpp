@@ -59,10 +59,12 @@ int main() {
       lo.coef = {f.coef[0], f.coef[1]};
       hi.coef = {f.coef[2], f.coef[3]};
       CommitmentKZG c0, c1;
-      std::thread t0([&] { c0 = commit_kzg_sharded(lo, r0); });
-      std::thread t1([&] { c1 = commit_kzg_sharded(hi, r1); });
+      std::string e0, e1;  // an exception must not escape a thread (std::terminate would lose the buffered output)
+      std::thread t0([&] { try { c0 = commit_kzg_sharded(lo, r0); } catch (const std::exception& e) { e0 = e.what(); } });
+      std::thread t1([&] { try { c1 = commit_kzg_sharded(hi, r1); } catch (const std::exception& e) { e1 = e.what(); } });
       t0.join();
       t1.join();
+      if (!e0.empty() || !e1.empty()) { printf("FAIL sharded commit threw: [%s] [%s]\n", e0.c_str(), e1.c_str()); return 1; }
       if (c0.xy != c.xy || c1.xy != c.xy) { printf("FAIL sharded commit\n"); return 1; }
     }
     printf("OK\n");

@@ -57,6 +57,7 @@ def test_field_ops(name, m):
     for x in vals:
         for y in rnd.sample(vals, 8) + edge:
             assert b2("mul", x, y) == x * y * rinv % m
+            assert b2("mul_k", x, y) == x * y * rinv % m
             assert b2("add", x, y) == (x + y) % m
             assert b2("sub", x, y) == (x - y) % m
         assert u1("neg", x) == (-x) % m
@@ -80,6 +81,9 @@ def test_field_ops(name, m):
                        else rnd.choice(edge) if rnd.random() < 0.2 else rnd.randrange(m)) for _ in range(4)]
         assert q4("mul2", x, y, z, w) == (x * y + z * w) * rinv % m
         assert q4("mul_sub_mul", x, y, z, w) == (x * y - z * w) * rinv % m
+        assert q4("mul2_k", x, y, z, w) == (x * y + z * w) * rinv % m
+        assert b2("mul_k", x, y) == x * y * rinv % m
+        assert b2("mul_k", z, w) == z * w * rinv % m
     for x in vals[:24]:
         exp = (pow(x, -1, m) if x else 0) * RR % m
         assert u1("inv", x * RR % m) == exp

@@ -526,9 +526,10 @@ def test_cpp_host_through_header_mirror():
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), "-o", exe, src,
                                "-L", os.path.join(root, "myzkp_b200"), "-lmyzkp_b200",
                                "-Wl,-rpath," + os.path.join(root, "myzkp_b200")])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = res.stdout
     vals = dict(line.split() for line in out.strip().splitlines() if " " in line)
-    assert out.strip().endswith("OK"), out
+    assert out.strip().endswith("OK"), f"rc={res.returncode} stdout={out!r} stderr={res.stderr[-2000:]!r}"
     assert int(vals["C.x"], 16) == 8096424998935924997123460782489249937183001369792870392058374165119638207724
     assert int(vals["C.y"], 16) == 14698683656276342473960081670169131092130433153277961881223581660609015832377
     assert int(vals["y"], 16) == 336

@@ -82,6 +82,13 @@ int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le /* n*64 */, si
  * [alpha^(first+i)]G for i < n; n = max_d + 1 (kzg.rs:32).  `first` lets a
  * rank generate only its shard of a range-sharded SRS. */
 int myzkp_srs_generate_g1(myzkp_ctx* ctx, const uint8_t alpha_le[32], size_t first, size_t n);
+/* G2 half of the public key, computed on the device and returned to the host (it is verifier-side and never
+ * needed resident): out[i] = [alpha^(first+i)] base for i < n, 128 B per point = x.c0 | x.c1 | y.c0 | y.c1
+ * (Fq2 = Fq[u]/(u^2+1), c0 + c1 u; 32 B little-endian canonical each; infinity = 128 zero bytes).
+ * base_or_null = NULL selects BN128::generator_g2() (bn128.rs:190-205).  n = 2 gives setup_kzg's
+ * powers_2 = [g2, [alpha]g2] (kzg.rs:37); n = max_d + 1 gives setup_kzg_with_full_g2's (kzg.rs:47-52). */
+int myzkp_srs_generate_g2(myzkp_ctx* ctx, const uint8_t alpha_le[32], const uint8_t* base_or_null /* 128 B */, size_t first,
+                          size_t n, uint8_t* out /* n*128 */);
 int myzkp_srs_read_g1(myzkp_ctx* ctx, size_t off, size_t n, uint8_t* out /* n*64 */);
 size_t myzkp_srs_len(const myzkp_ctx* ctx);
 

@@ -22,6 +22,14 @@ struct G1Point {                         // EllipticCurvePoint<Fq, BN128Curve> (
   }
   bool operator==(const G1Point& o) const { return xy == o.xy; }
 };
+struct G2Point {                         // EllipticCurvePoint<Fq2, BN128Curve> (bn128.rs:49); all-zero = infinity
+  std::array<uint8_t, 128> xy{};         // x.c0 | x.c1 | y.c0 | y.c1, 32 B little-endian canonical each
+  bool is_point_at_infinity() const {
+    for (uint8_t b : xy) if (b) return false;
+    return true;
+  }
+  bool operator==(const G2Point& o) const { return xy == o.xy; }
+};
 struct Polynomial {                      // Polynomial<FqOrder> (polynomial.rs:69-74), low -> high degree
   std::vector<Scalar> coef;
 };
@@ -57,6 +65,14 @@ class PublicKeyKZG {                     // kzg.rs:8-11; powers_1 resident on th
 // setup_kzg (kzg.rs:27-40) with alpha injected; max_d + 1 powers of the standard generator
 inline void setup_kzg(PublicKeyKZG& pk, size_t max_d, const Scalar& alpha) {
   pk.check(myzkp_srs_generate_g1(pk.ctx(), alpha.data(), 0, max_d + 1));
+}
+// powers_2 of the public key: [alpha^i] g2 for i < n, g2 = BN128::generator_g2() when `base` is null
+// (n = 2: setup_kzg, kzg.rs:37; n = max_d + 1: setup_kzg_with_full_g2, kzg.rs:47-52)
+inline std::vector<G2Point> powers_2(const PublicKeyKZG& pk, const Scalar& alpha, size_t n, const G2Point* base = nullptr) {
+  std::vector<G2Point> out(n);
+  pk.check(myzkp_srs_generate_g2(pk.ctx(), alpha.data(), base ? base->xy.data() : nullptr, 0, n,
+                                 out.empty() ? nullptr : out[0].xy.data()));
+  return out;
 }
 // commit_kzg (kzg.rs:57-59)
 inline CommitmentKZG commit_kzg(const Polynomial& f, const PublicKeyKZG& pk) {

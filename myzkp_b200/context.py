@@ -44,6 +44,20 @@ def point_to_bytes(pt) -> bytes:
     return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
 
 
+def g2_to_bytes(pt) -> bytes:
+    """G2 wire form: x.c0 | x.c1 | y.c0 | y.c1 (32 B little-endian canonical each); infinity = 128 zero bytes."""
+    if pt is None:
+        return bytes(128)
+    (x0, x1), (y0, y1) = pt
+    return b"".join((int(v) % P_MOD).to_bytes(32, "little") for v in (x0, x1, y0, y1))
+
+
+def g2_from_bytes(b):
+    b = bytes(b)
+    v = [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(4)]
+    return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -126,6 +140,17 @@ class Context:
     def srs_generate(self, alpha: int, n: int, first: int = 0):
         a = np.frombuffer(int(alpha % R_MOD).to_bytes(32, "little"), dtype=np.uint8).copy()
         self._ck(self._lib.myzkp_srs_generate_g1(self.h, _ptr(a), first, n))
+
+    def srs_generate_g2(self, alpha: int, n: int, first: int = 0, base=None):
+        """[alpha^(first+i)] base for i < n on G2 as ((x.c0, x.c1), (y.c0, y.c1)) tuples / None for infinity;
+        base = None is BN128::generator_g2()."""
+        a = np.frombuffer(int(alpha % R_MOD).to_bytes(32, "little"), dtype=np.uint8).copy()
+        b = None
+        if base is not None:
+            b = np.frombuffer(g2_to_bytes(base), dtype=np.uint8).copy()
+        out = np.zeros((n, 128), np.uint8)
+        self._ck(self._lib.myzkp_srs_generate_g2(self.h, _ptr(a), _ptr(b) if b is not None else None, first, n, _ptr(out)))
+        return [g2_from_bytes(out[i]) for i in range(n)]
 
     def srs_load(self, points: Sequence):
         """points: list of (x, y) / None, or an (n,64) uint8 array."""

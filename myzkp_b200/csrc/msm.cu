@@ -534,9 +534,13 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
   const uint32_t nb = 1u << (c - 1);
   const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
   const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
-  // chunk length: about one wave of (3 blocks x 128 threads) per SM
-  uint32_t Lb = 8;
-  while (Lb < 64 && (uint64_t)nb * K / Lb > (uint64_t)ctx->sm_count * 3 * 128) Lb *= 2;
+  // chunk length, from a sweep on B200 (profiles/experiments_r1.md): two blocks of 128 threads per SM
+  // (more warps per sub-partition made the kernel slower, fewer left SMs idle), at least 4 buckets
+  // per thread (each thread also pays a ~30-operation double-and-add by its chunk offset)
+  const uint64_t target = (uint64_t)ctx->sm_count * 2 * 128;
+  uint32_t Lb = (uint32_t)(((uint64_t)nb * K + target - 1) / target);
+  if (Lb < 4) Lb = 4;
+  if (Lb > 256) Lb = 256;
   if (Lb > nb) Lb = nb;
   uint32_t nchunks = (nb + Lb - 1) / Lb;
   MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)K * nchunks * sizeof(XYZZ)));

@@ -47,12 +47,52 @@ class G1Point:
         return f"G1Point({self.as_tuple()})"
 
 
+class G2Point:
+    """EllipticCurvePoint<Fq2, BN128Curve> (curve/bn128.rs:49): affine over Fq2 = Fq[u]/(u^2 + 1);
+    a coordinate is the pair (c0, c1) of the reference's polynomial coefficients; infinity = (None, None)."""
+
+    __slots__ = ("x", "y")
+
+    def __init__(self, x=None, y=None):
+        self.x = None if x is None else (int(x[0]) % P_MOD, int(x[1]) % P_MOD)
+        self.y = None if y is None else (int(y[0]) % P_MOD, int(y[1]) % P_MOD)
+
+    @staticmethod
+    def point_at_infinity() -> "G2Point":
+        return G2Point(None, None)
+
+    def is_point_at_infinity(self) -> bool:
+        return self.x is None or self.y is None
+
+    @staticmethod
+    def _from_tuple(t) -> "G2Point":
+        return G2Point(None, None) if t is None else G2Point(t[0], t[1])
+
+    def as_tuple(self):
+        return None if self.is_point_at_infinity() else (self.x, self.y)
+
+    def __eq__(self, o):
+        return isinstance(o, G2Point) and self.as_tuple() == o.as_tuple()
+
+    def __repr__(self):
+        return f"G2Point({self.as_tuple()})"
+
+
 class BN128:
-    """curve/bn128.rs:183-212 (G1 side only)."""
+    """curve/bn128.rs:183-212."""
 
     @staticmethod
     def generator_g1() -> G1Point:
         return G1Point(1, 2)
+
+    @staticmethod
+    def generator_g2() -> G2Point:
+        """bn128.rs:190-205."""
+        return G2Point(
+            (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+             11559732032986387107991004021392285783925812861821192530917403151452391805634),
+            (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+             4082367875863433681332203403145435568316851327593401208105741076214120093531))
 
     @staticmethod
     def order() -> int:
@@ -79,11 +119,12 @@ class Polynomial:
 
 
 class PublicKeyKZG:
-    """kzg.rs:8-11.  powers_1 lives on the GPU as the resident SRS table;
-    powers_2 (G2) is verifier-side and out of scope."""
+    """kzg.rs:8-11.  powers_1 lives on the GPU as the resident SRS table; powers_2 (G2, used by the
+    verifier only) is computed on the GPU at setup and kept on the host."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, powers_2: Optional[List[G2Point]] = None):
         self.ctx = ctx
+        self.powers_2 = powers_2 if powers_2 is not None else []
 
     @property
     def powers_1(self) -> List[G1Point]:
@@ -104,19 +145,35 @@ class ProofKZG:
 CommitmentKZG = G1Point
 
 
-def setup_kzg(g1: G1Point, g2=None, max_d: int = 0, *, alpha: Optional[int] = None, ctx: Optional[Context] = None,
-              device: int = 0) -> PublicKeyKZG:
-    """kzg.rs:27-40: max_d + 1 powers [alpha^i]g1.  The reference draws alpha from
-    an unseeded thread_rng (field.rs:198-206); pass `alpha` for reproducibility.
-    Only the standard generator is supported on the device path; any other base
-    point is handled by loading explicit powers with PublicKeyKZG/ctx.srs_load."""
+def _setup(g1: G1Point, g2: Optional[G2Point], max_d: int, n_g2: int, alpha, ctx, device) -> PublicKeyKZG:
     if g1 != BN128.generator_g1():
         raise ValueError("setup_kzg on the GPU path generates powers of BN128::generator_g1(); load other SRS with Context.srs_load")
     if alpha is None:
         alpha = secrets.randbelow(R_MOD)
     ctx = ctx or Context(device)
     ctx.srs_generate(alpha, max_d + 1)
-    return PublicKeyKZG(ctx)
+    base = None if g2 is None or g2 == BN128.generator_g2() else g2.as_tuple()
+    if g2 is not None and g2.is_point_at_infinity():
+        p2 = [None] * n_g2
+    else:
+        p2 = ctx.srs_generate_g2(alpha, n_g2, 0, base)
+    return PublicKeyKZG(ctx, [G2Point._from_tuple(t) for t in p2])
+
+
+def setup_kzg(g1: G1Point, g2: Optional[G2Point] = None, max_d: int = 0, *, alpha: Optional[int] = None,
+              ctx: Optional[Context] = None, device: int = 0) -> PublicKeyKZG:
+    """kzg.rs:27-40: max_d + 1 powers [alpha^i]g1 and powers_2 = [g2, [alpha]g2].  The reference draws
+    alpha from an unseeded thread_rng (field.rs:198-206); pass `alpha` for reproducibility.  g2 = None
+    means BN128::generator_g2(); any G2 base point is accepted.  On the G1 side only the standard
+    generator is supported on the device path; any other base is handled by loading explicit powers
+    with Context.srs_load."""
+    return _setup(g1, g2, max_d, 2, alpha, ctx, device)
+
+
+def setup_kzg_with_full_g2(g1: G1Point, g2: Optional[G2Point] = None, max_d: int = 0, *, alpha: Optional[int] = None,
+                           ctx: Optional[Context] = None, device: int = 0) -> PublicKeyKZG:
+    """kzg.rs:42-55: as setup_kzg, with powers_2 = [alpha^i]g2 for i = 0..=max_d."""
+    return _setup(g1, g2, max_d, max_d + 1, alpha, ctx, device)
 
 
 def commit_kzg(f: Polynomial, pk: PublicKeyKZG) -> CommitmentKZG:

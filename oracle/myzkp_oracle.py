@@ -181,31 +181,33 @@ class G1Point:
     infinity = (None, None), no on-curve check (curve.rs:26-28)."""
 
     __slots__ = ("x", "y")
+    F = Fq  # coordinate field (EllipticCurvePoint is generic over it, curve.rs:17-24)
 
     def __init__(self, x: Optional[Fq], y: Optional[Fq]):
         self.x = x
         self.y = y
 
-    @staticmethod
-    def new(x: Fq, y: Fq) -> "G1Point":
-        return G1Point(x, y)
+    @classmethod
+    def new(cls, x, y):
+        return cls(x, y)
 
-    @staticmethod
-    def point_at_infinity() -> "G1Point":
-        return G1Point(None, None)
+    @classmethod
+    def point_at_infinity(cls):
+        return cls(None, None)
 
     def is_point_at_infinity(self) -> bool:
         return self.x is None or self.y is None
 
-    def clone(self) -> "G1Point":
-        return G1Point(self.x, self.y)
+    def clone(self):
+        return type(self)(self.x, self.y)
 
     def line_slope(self, other: "G1Point") -> Fq:
         """curve.rs:56-70."""
-        a = Fq.from_value(CURVE_A)
+        F = self.F
+        a = F.from_value(CURVE_A)
         x1, y1, x2, y2 = self.x, self.y, other.x, other.y
         if self.x == other.x:
-            return (x1.mul_ref(x1) * Fq.from_value(3) + a) / (y1.mul_ref(Fq.from_value(2)))
+            return (x1.mul_ref(x1) * F.from_value(3) + a) / (y1.mul_ref(F.from_value(2)))
         return y2.sub_ref(y1) / x2.sub_ref(x1)
 
     def double(self) -> "G1Point":
@@ -216,7 +218,7 @@ class G1Point:
         x, y = self.x, self.y
         new_x = slope.mul_ref(slope).sub_ref(x).sub_ref(x)
         new_y = -slope.mul_ref(new_x) + slope * x - y
-        return G1Point(new_x, new_y)
+        return type(self)(new_x, new_y)
 
     def inplace_double(self) -> None:
         """curve.rs:87-101."""
@@ -232,12 +234,12 @@ class G1Point:
         if self.x == other.x and self.y == other.y:
             return self.double()
         elif self.x == other.x:
-            return G1Point.point_at_infinity()
+            return type(self).point_at_infinity()
         slope = self.line_slope(other)
         x1, y1, x2 = self.x, self.y, other.x
         new_x = slope.mul_ref(slope).sub_ref(x1).sub_ref(x2)
         new_y = (-slope).mul_ref(new_x) + slope.mul_ref(x1).sub_ref(y1)
-        return G1Point(new_x, new_y)
+        return type(self)(new_x, new_y)
 
     def add_assign_ref(self, other: "G1Point") -> None:
         """curve.rs:130-161."""
@@ -247,10 +249,10 @@ class G1Point:
     def mul_ref(self, scalar: int) -> "G1Point":
         """curve.rs:163-191: LSB-first double-and-add; 0 -> infinity; negative panics."""
         if scalar == 0:
-            return G1Point.point_at_infinity()
+            return type(self).point_at_infinity()
         if scalar < 0:
             raise ValueError("multiplier should be non-negative")  # curve.rs:174-176
-        result = G1Point.point_at_infinity()
+        result = type(self).point_at_infinity()
         current = self.clone()
         bits = scalar
         while bits != 0:
@@ -263,7 +265,7 @@ class G1Point:
     def __neg__(self):  # curve.rs:216-225
         if self.is_point_at_infinity():
             return self
-        return G1Point(self.x, -self.y)
+        return type(self)(self.x, -self.y)
 
     def __add__(self, o):
         return self.add_ref(o)
@@ -275,7 +277,7 @@ class G1Point:
         return self.mul_ref(k)
 
     def __eq__(self, o) -> bool:
-        if not isinstance(o, G1Point):
+        if type(o) is not type(self):
             return False
         if self.is_point_at_infinity() or o.is_point_at_infinity():
             return self.is_point_at_infinity() and o.is_point_at_infinity()
@@ -545,6 +547,224 @@ def open_gemini(polys: Sequence[Polynomial], beta: Fr, pk: PublicKeyKZG) -> Proo
     es = [batch_open_kzg(p, [beta, (Fr.zero() - beta).sanitize(), beta.pow(2)], pk) for p in polys[: num_polys - 1]]
     degree_proofs = [prove_degree_bound(p, pk, 2 ** (num_polys - i - 1)) for i, p in enumerate(polys)]
     return ProofGemini(es, degree_proofs)
+
+# --- G2: the same curve law over Fq2 = Fq[x] / (x^2 + 1) ----------------------
+class Fq2:
+    """ExtendedFieldElement<BN128Modulus, Fq2Poly> (efield.rs:93-118, bn128.rs:33-49): a polynomial
+    over Fq kept reduced modulo x^2 + 1; `c` = [c0, c1] low -> high (canonical ints, always length 2
+    here; the reference trims trailing zeros, which does not change the value)."""
+
+    __slots__ = ("c",)
+
+    def __init__(self, c: Sequence[int]):
+        # efield.rs:103-108: poly % (x^2 + 1), i.e. x^2 = -1, x^3 = -x, x^4 = 1, ...
+        lo = [0, 0]
+        for i, v in enumerate(c):
+            lo[i % 2] += -int(v) if (i // 2) % 2 else int(v)
+        lo = [lo[0] % P_MOD, lo[1] % P_MOD]
+        self.c = lo
+
+    @classmethod
+    def from_value(cls, v: int) -> "Fq2":  # from_base_field, efield.rs:115-117
+        return cls([v])
+
+    @classmethod
+    def zero(cls):
+        return cls([0])
+
+    @classmethod
+    def one(cls):
+        return cls([1])
+
+    def is_zero(self) -> bool:
+        return self.c == [0, 0]
+
+    def add_ref(self, o: "Fq2") -> "Fq2":  # efield.rs:342-344
+        return Fq2([self.c[0] + o.c[0], self.c[1] + o.c[1]])
+
+    def sub_ref(self, o: "Fq2") -> "Fq2":  # efield.rs:360-362
+        return Fq2([self.c[0] - o.c[0], self.c[1] - o.c[1]])
+
+    def mul_ref(self, o: "Fq2") -> "Fq2":  # efield.rs:351-353: polynomial product, then new() reduces
+        a, b = self.c, o.c
+        return Fq2([a[0] * b[0], a[0] * b[1] + a[1] * b[0], a[1] * b[1]])
+
+    def inverse(self) -> "Fq2":
+        """efield.rs:126-151: extended Euclid on polynomials (low, high) = (self, x^2 + 1)."""
+        lm, hm = [1], [0]
+        low, high = _ptrim(list(self.c)), [1, 0, 1]
+        while low:
+            q, r = _pdivmod(high, low)
+            nm = _psub(hm, _pmul(lm, q))
+            high, hm, low, lm = low, lm, r, nm
+        inv0 = Fq.from_value(high[0]).inverse().sanitize().value
+        return Fq2([v * inv0 for v in hm])
+
+    def div_ref(self, o: "Fq2") -> "Fq2":  # efield.rs:153-155
+        return self.mul_ref(o.inverse())
+
+    def __eq__(self, o) -> bool:  # efield.rs:199-205
+        return isinstance(o, Fq2) and self.c == o.c
+
+    def __hash__(self):
+        return hash(tuple(self.c))
+
+    def __add__(self, o):
+        return self.add_ref(o)
+
+    def __sub__(self, o):
+        return self.sub_ref(o)
+
+    def __mul__(self, o):
+        return self.mul_ref(o)
+
+    def __neg__(self):  # efield.rs:329-337
+        return Fq2([-self.c[0], -self.c[1]])
+
+    def __truediv__(self, o):
+        return self.div_ref(o)
+
+    def sanitize(self) -> "Fq2":
+        return self
+
+    def __repr__(self):
+        return f"Fq2({self.c})"
+
+
+def _ptrim(a: List[int]) -> List[int]:
+    a = [v % P_MOD for v in a]
+    while a and a[-1] == 0:
+        a.pop()
+    return a
+
+
+def _pmul(a: List[int], b: List[int]) -> List[int]:
+    out = [0] * max(0, len(a) + len(b) - 1)
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            out[i + j] = (out[i + j] + x * y) % P_MOD
+    return _ptrim(out)
+
+
+def _psub(a: List[int], b: List[int]) -> List[int]:
+    n = max(len(a), len(b))
+    return _ptrim([(a[i] if i < len(a) else 0) - (b[i] if i < len(b) else 0) for i in range(n)])
+
+
+def _pdivmod(a: List[int], b: List[int]) -> Tuple[List[int], List[int]]:
+    """Polynomial long division over Fq (polynomial.rs:371-405)."""
+    a, b = _ptrim(list(a)), _ptrim(list(b))
+    if len(a) < len(b):
+        return [], a
+    q = [0] * (len(a) - len(b) + 1)
+    lead_inv = Fq.from_value(b[-1]).inverse().sanitize().value
+    r = list(a)
+    while len(r) >= len(b) and r:
+        shift = len(r) - len(b)
+        coef = r[-1] * lead_inv % P_MOD
+        q[shift] = coef
+        for i, v in enumerate(b):
+            r[shift + i] = (r[shift + i] - coef * v) % P_MOD
+        r = _ptrim(r)
+    return _ptrim(q), r
+
+
+class G2Point(G1Point):
+    """EllipticCurvePoint<Fq2, BN128Curve> (bn128.rs:49): curve.rs's affine law with a = 0 over Fq2."""
+
+    __slots__ = ()
+    F = Fq2
+
+    def affine_ints(self):
+        """((x.c0, x.c1), (y.c0, y.c1)) canonical, or None for infinity."""
+        if self.is_point_at_infinity():
+            return None
+        return (tuple(self.x.c), tuple(self.y.c))
+
+    def __repr__(self):
+        return f"G2Point({self.affine_ints()})"
+
+
+G2_GEN_X = (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+            11559732032986387107991004021392285783925812861821192530917403151452391805634)
+G2_GEN_Y = (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+            4082367875863433681332203403145435568316851327593401208105741076214120093531)
+
+
+def generator_g2() -> G2Point:
+    """bn128.rs:190-205."""
+    return G2Point.new(Fq2(G2_GEN_X), Fq2(G2_GEN_Y))
+
+
+def get_b2() -> Fq2:
+    """bn128.rs:218-224: 3 / (9 + x)."""
+    return Fq2([3]) / Fq2([9, 1])
+
+
+def setup_kzg_g2(g2: G2Point, alpha: int, n: int) -> List[G2Point]:
+    """powers_2 of kzg.rs:27-55 with alpha injected: n = 2 for setup_kzg ([g2, [alpha]g2], kzg.rs:37),
+    n = max_d + 1 for setup_kzg_with_full_g2 (kzg.rs:47-52)."""
+    a = Fr.from_value(alpha)
+    out, alpha_power = [], Fr.one()
+    for _ in range(n):
+        out.append(g2.mul_ref(alpha_power.sanitize().get_value()))
+        alpha_power = alpha_power * a
+    return out
+
+
+# fast independent path for G2 (Jacobian over Fq2 as int pairs) - used for larger checks
+def _f2mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % P_MOD, (a[0] * b[1] + a[1] * b[0]) % P_MOD)
+
+
+def _f2inv(a):
+    n = pow(a[0] * a[0] + a[1] * a[1], -1, P_MOD)
+    return (a[0] * n % P_MOD, -a[1] * n % P_MOD)
+
+
+def _g2_fast_add(p1, p2):
+    if p1 is None:
+        return p2
+    if p2 is None:
+        return p1
+    (x1, y1), (x2, y2) = p1, p2
+    if x1 == x2:
+        if (y1[0] + y2[0]) % P_MOD == 0 and (y1[1] + y2[1]) % P_MOD == 0:
+            return None
+        xx = _f2mul(x1, x1)
+        lam = _f2mul((3 * xx[0] % P_MOD, 3 * xx[1] % P_MOD), _f2inv((2 * y1[0] % P_MOD, 2 * y1[1] % P_MOD)))
+    else:
+        lam = _f2mul(((y2[0] - y1[0]) % P_MOD, (y2[1] - y1[1]) % P_MOD), _f2inv(((x2[0] - x1[0]) % P_MOD, (x2[1] - x1[1]) % P_MOD)))
+    l2 = _f2mul(lam, lam)
+    x3 = ((l2[0] - x1[0] - x2[0]) % P_MOD, (l2[1] - x1[1] - x2[1]) % P_MOD)
+    t = _f2mul(lam, ((x1[0] - x3[0]) % P_MOD, (x1[1] - x3[1]) % P_MOD))
+    return (x3, ((t[0] - y1[0]) % P_MOD, (t[1] - y1[1]) % P_MOD))
+
+
+def g2_fast_mul(k: int, pt=(G2_GEN_X, G2_GEN_Y)):
+    """[k mod r] pt on G2 as ((x0, x1), (y0, y1)) or None."""
+    k %= R_MOD
+    acc, cur = None, pt
+    while k:
+        if k & 1:
+            acc = _g2_fast_add(acc, cur)
+        cur = _g2_fast_add(cur, cur)
+        k >>= 1
+    return acc
+
+
+def g2_to_bytes(pt) -> bytes:
+    """Wire form: x.c0 | x.c1 | y.c0 | y.c1, 32 B little-endian each; infinity = 128 zero bytes."""
+    if pt is None:
+        return bytes(128)
+    (x0, x1), (y0, y1) = pt
+    return b"".join(int(v).to_bytes(32, "little") for v in (x0, x1, y0, y1))
+
+
+def g2_from_bytes(b: bytes):
+    v = [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(4)]
+    return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+
 
 
 # --- O(N) algebraic expected values for sizes the naive path cannot reach ---

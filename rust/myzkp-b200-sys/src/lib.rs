@@ -32,6 +32,8 @@ extern "C" {
     pub fn myzkp_srs_load_g1(ctx: *mut myzkp_ctx, affine_xy_le: *const u8, n: usize) -> c_int;
     pub fn myzkp_srs_generate_g1(ctx: *mut myzkp_ctx, alpha_le: *const u8, first: usize, n: usize) -> c_int;
     pub fn myzkp_srs_read_g1(ctx: *mut myzkp_ctx, off: usize, n: usize, out: *mut u8) -> c_int;
+    pub fn myzkp_srs_generate_g2(ctx: *mut myzkp_ctx, alpha_le: *const u8, base_or_null: *const u8, first: usize, n: usize,
+                                 out: *mut u8) -> c_int;
     pub fn myzkp_srs_len(ctx: *const myzkp_ctx) -> usize;
 
     pub fn myzkp_kzg_commit(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, out_c: *mut u8) -> c_int;

@@ -6,7 +6,7 @@
 use std::ffi::CStr;
 use std::ptr;
 
-use myzkp::modules::algebra::curve::bn128::{Fq, FqOrder, G1Point, G2Point, BN128};
+use myzkp::modules::algebra::curve::bn128::{Fq, Fq2, FqOrder, G1Point, G2Point, BN128};
 use myzkp::modules::algebra::field::Field;
 use myzkp::modules::algebra::polynomial::Polynomial;
 use myzkp::modules::algebra::ring::Ring;
@@ -66,8 +66,48 @@ fn point_from_bytes(b: &[u8; 64]) -> G1Point {
     G1Point::new(Fq::from_value(x), Fq::from_value(y))
 }
 
-/// setup_kzg (kzg.rs:27-40).  `g1` must be BN128::generator_g1(); alpha is drawn like the reference does.
-pub fn setup_kzg(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPublicKeyKZG {
+fn fq_to_le(x: &Fq) -> [u8; 32] {
+    let (_, digits) = x.sanitize().get_value().to_u64_digits();
+    let mut out = [0u8; 32];
+    for (i, d) in digits.iter().take(4).enumerate() {
+        out[8 * i..8 * i + 8].copy_from_slice(&d.to_le_bytes());
+    }
+    out
+}
+
+/// G2 wire form: x.c0 | x.c1 | y.c0 | y.c1 (Fq2 = Fq[u]/(u^2+1), efield.rs:95-98: `poly.coef` low -> high,
+/// trailing zeros trimmed); infinity = 128 zero bytes.
+fn g2_to_bytes(p: &G2Point) -> [u8; 128] {
+    let mut out = [0u8; 128];
+    if let (Some(x), Some(y)) = (&p.x, &p.y) {
+        for (k, e) in [x, y].iter().enumerate() {
+            for (j, c) in e.poly.coef.iter().take(2).enumerate() {
+                out[64 * k + 32 * j..64 * k + 32 * j + 32].copy_from_slice(&fq_to_le(c));
+            }
+        }
+    }
+    out
+}
+
+fn g2_from_bytes(b: &[u8]) -> G2Point {
+    if b.iter().all(|&x| x == 0) {
+        return G2Point::point_at_infinity();
+    }
+    let fq = |s: &[u8]| Fq::from_value(BigInt::from_bytes_le(Sign::Plus, s));
+    let fq2 = |s: &[u8]| Fq2::new(Polynomial { coef: vec![fq(&s[..32]), fq(&s[32..64])] });
+    G2Point::new(fq2(&b[..64]), fq2(&b[64..128]))
+}
+
+/// [alpha^i] g2 for i < n, computed on the GPU (kzg.rs:37 for n = 2, kzg.rs:47-52 for n = max_d + 1)
+fn g2_powers(ctx: *mut sys::myzkp_ctx, alpha: &FqOrder, g2: &G2Point, n: usize) -> Vec<G2Point> {
+    let a = scalar_to_le(alpha);
+    let base = g2_to_bytes(g2);
+    let mut out = vec![0u8; 128 * n];
+    check(ctx, unsafe { sys::myzkp_srs_generate_g2(ctx, a.as_ptr(), base.as_ptr(), 0, n, out.as_mut_ptr()) });
+    out.chunks_exact(128).map(g2_from_bytes).collect()
+}
+
+fn setup(g1: &G1Point, g2: &G2Point, max_d: usize, n_g2: usize) -> GpuPublicKeyKZG {
     assert!(*g1 == BN128::generator_g1());
     let alpha = FqOrder::random_element(&[]); // kzg.rs:28
     let mut ctx = ptr::null_mut();
@@ -75,8 +115,18 @@ pub fn setup_kzg(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPublicKeyKZG {
     assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
     let a = scalar_to_le(&alpha);
     check(ctx, unsafe { sys::myzkp_srs_generate_g1(ctx, a.as_ptr(), 0, max_d + 1) });
-    let powers_2 = vec![g2.clone(), g2.mul_ref(alpha.get_value())]; // kzg.rs:37 (CPU, verifier side)
+    let powers_2 = g2_powers(ctx, &alpha, g2, n_g2);
     GpuPublicKeyKZG { ctx, powers_2 }
+}
+
+/// setup_kzg (kzg.rs:27-40).  `g1` must be BN128::generator_g1(); alpha is drawn like the reference does.
+pub fn setup_kzg(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPublicKeyKZG {
+    setup(g1, g2, max_d, 2) // powers_2 = [g2, [alpha]g2], kzg.rs:37
+}
+
+/// setup_kzg_with_full_g2 (kzg.rs:42-55): powers_2 = [alpha^i]g2 for i = 0..=max_d
+pub fn setup_kzg_with_full_g2(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPublicKeyKZG {
+    setup(g1, g2, max_d, max_d + 1)
 }
 
 /// commit_kzg (kzg.rs:57-59)
@@ -118,7 +168,8 @@ pub fn setup_kzg_range(device: i32, alpha: &FqOrder, first: usize, count: usize,
     assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
     let a = scalar_to_le(alpha);
     check(ctx, unsafe { sys::myzkp_srs_generate_g1(ctx, a.as_ptr(), first, count) });
-    GpuPublicKeyKZG { ctx, powers_2: vec![g2.clone(), g2.mul_ref(alpha.get_value())] }
+    let powers_2 = g2_powers(ctx, alpha, g2, 2);
+    GpuPublicKeyKZG { ctx, powers_2 }
 }
 
 /// Map every rank's exchange buffer into every other rank (all ranks in this process).

@@ -49,6 +49,12 @@ int main() {
       printf("FAIL commit_gemini batch\n");
       return 1;
     }
+    // G2 half of the key: [g2, [alpha]g2]; alpha^0 = 1 gives the generator back, 2 * g2 is a public vector
+    {
+      auto p2 = powers_2(pk, scalar_u64(2), 2);
+      printf("G2.2x0 %s\n", hex_be(p2[1].xy.data()).c_str());
+      if (p2.size() != 2 || p2[0].is_point_at_infinity() || p2[1] == p2[0]) { printf("FAIL powers_2\n"); return 1; }
+    }
     // range-sharded commit inside one process: two ranks (own threads), exchange over peer memory
     {
       PublicKeyKZG r0(0), r1(0);

@@ -19,7 +19,7 @@ RR = 1 << 256
 def _build(name):
     src = os.path.join(HERE, "emul", f"{name}.cpp")
     out = os.path.join(HERE, "emul", f"lib{name}.so")
-    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh")]
+    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh", "g2.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)
@@ -178,3 +178,46 @@ def test_batched_affine_rounds_emulated():
                     x, y = fl(out, 16 * b) * rinv % P, fl(out, 16 * b + 8) * rinv % P
                     got.append(None if (x, y) == (0, 0) else (x, y))
                 assert got == exp, (trial, seg, rounds, fused)
+
+
+def test_g2_group_law_emulated():
+    """csrc/g2.cuh (Fq2, Jacobian G2, scalar multiplication) against the oracle's restatement of the
+    reference's affine law over Fq2 (curve.rs:56-191 with efield.rs) and its fast cross-check."""
+    L = _build("emul_g2")
+    rnd = random.Random(11)
+    A32 = ctypes.c_uint32 * 32
+
+    def enc(pt):
+        if pt is None:
+            return A32()
+        vals = [pt[0][0], pt[0][1], pt[1][0], pt[1][1]]
+        return A32(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vals for i in range(8)])
+
+    def dec(a):
+        v = [fl(a, 8 * i) for i in range(4)]
+        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+
+    gen = (o.G2_GEN_X, o.G2_GEN_Y)
+    g = o.generator_g2()
+    for k in [0, 1, 2, 3, 5, 12345, R - 1, R - 2, R, R + 7, (1 << 254) - 1, (1 << 256) - 1] + [rnd.randrange(R) for _ in range(6)]:
+        out = A32()
+        L.emul_g2_scalar_mul(enc(gen), tl(k), out)
+        assert dec(out) == o.g2_fast_mul(k), k
+    # the faithful (affine, ext-Euclid) oracle on small multipliers, incl. kzg.rs:37's [g2, [alpha]g2]
+    for k in [1, 2, 9, 14, 123456789]:
+        out = A32()
+        L.emul_g2_scalar_mul(enc(gen), tl(k), out)
+        assert dec(out) == g.mul_ref(k).affine_ints()
+    # special cases of the addition (curve.rs:103-161)
+    pts = [o.g2_fast_mul(rnd.randrange(1, R)) for _ in range(4)] + [gen, o.g2_fast_mul(2), None]
+    neg = lambda p: None if p is None else (p[0], ((-p[1][0]) % P, (-p[1][1]) % P))
+    for a in pts:
+        for b in pts + [neg(a)]:
+            out = A32()
+            L.emul_g2_add(enc(a), enc(b), out)
+            assert dec(out) == o._g2_fast_add(a, b)
+    for _ in range(20):
+        x = (rnd.randrange(P), rnd.randrange(P))
+        out = (ctypes.c_uint32 * 16)()
+        L.emul_fq2_inv((ctypes.c_uint32 * 16)(*[(v >> (32 * i)) & 0xFFFFFFFF for v in x for i in range(8)]), out)
+        assert (fl(out), fl(out, 8)) == tuple((o.Fq2(list(x)).inverse()).c)

@@ -515,6 +515,41 @@ def test_generic_msm_with_caller_points(ctx):
     assert ctx.g1_msm(coefs) == o.expected_commit(coefs, alpha) == ctx.commit(coefs)
 
 
+def test_g2_powers_of_the_public_key(ctx):
+    """setup_kzg's powers_2 = [g2, [alpha]g2] (kzg.rs:37) and setup_kzg_with_full_g2's [alpha^i]g2
+    (kzg.rs:47-52), computed on the device, bit-exact vs the oracle's restatement of the reference's
+    affine law over Fq2 (small cases) and its fast cross-check (larger ones)."""
+    alpha = synth.random_scalar(synth.SEED_ALPHA)
+    pk = mz.setup_kzg(mz.BN128.generator_g1(), mz.BN128.generator_g2(), 7, alpha=alpha, ctx=ctx)
+    assert len(pk.powers_2) == 2
+    assert pk.powers_2[0] == mz.BN128.generator_g2()
+    assert pk.powers_2[1].as_tuple() == o.g2_fast_mul(alpha)
+    assert pk.powers_2[1].as_tuple() == o.setup_kzg_g2(o.generator_g2(), alpha, 2)[1].affine_ints()  # faithful path
+    pk = mz.setup_kzg_with_full_g2(mz.BN128.generator_g1(), None, 40, alpha=alpha, ctx=ctx)
+    assert len(pk) == 41 and len(pk.powers_2) == 41
+    for i, p in enumerate(pk.powers_2):
+        assert p.as_tuple() == o.g2_fast_mul(pow(alpha, i, R)), i
+    # window into the powers, an arbitrary base point, a small alpha against the faithful oracle
+    base = o.g2_fast_mul(0xABCDEF)
+    got = ctx.srs_generate_g2(3, 5, first=2, base=base)
+    assert got == [o.g2_fast_mul(3 ** (2 + i), base) for i in range(5)]
+    assert got[0] == o.G2Point.new(o.Fq2(base[0]), o.Fq2(base[1])).mul_ref(9).affine_ints()
+    # alpha = 0: [g2, infinity, ...]; infinity as base stays infinity; the G1 and G2 halves share alpha
+    assert ctx.srs_generate_g2(0, 3) == [(o.G2_GEN_X, o.G2_GEN_Y), None, None]
+    assert ctx.srs_generate_g2(5, 2, base=None)[1] == o.g2_fast_mul(5)
+    pk = mz.setup_kzg(mz.BN128.generator_g1(), mz.G2Point.point_at_infinity(), 1, alpha=alpha, ctx=ctx)
+    assert all(p.is_point_at_infinity() for p in pk.powers_2)
+    # non-canonical coordinates are rejected
+    bad = np.zeros(128, np.uint8)
+    bad[:32] = 0xFF
+    a = np.frombuffer(int(5).to_bytes(32, "little"), dtype=np.uint8).copy()
+    out = np.zeros(128, np.uint8)
+    import ctypes
+    code = ctx._lib.myzkp_srs_generate_g2(ctx.h, a.ctypes.data_as(ctypes.c_void_p), bad.ctypes.data_as(ctypes.c_void_p), 0, 1,
+                                          out.ctypes.data_as(ctypes.c_void_p))
+    assert code != 0
+
+
 def test_cpp_host_through_header_mirror():
     """tests/cpp/abi_smoke.cpp: a C++ host over include/myzkp_b200.hpp reproduces the test_kzg anchor."""
     import subprocess
@@ -533,5 +568,6 @@ def test_cpp_host_through_header_mirror():
     assert int(vals["C.x"], 16) == 8096424998935924997123460782489249937183001369792870392058374165119638207724
     assert int(vals["C.y"], 16) == 14698683656276342473960081670169131092130433153277961881223581660609015832377
     assert int(vals["y"], 16) == 336
+    assert int(vals["G2.2x0"], 16) == 18029695676650738226693292988307914797657423701064905010927197838374790804409
     assert int(vals["W.x"], 16) == 15737316170989375530370354340609809222984715696988518295913516551941326522818
     assert int(vals["W.y"], 16) == 13254863773102499080085687663253363332659578358445016579269372167128026496803

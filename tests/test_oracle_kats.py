@@ -115,3 +115,32 @@ def test_fast_paths_agree_with_faithful():
     assert o.commit_kzg(f, pk).affine_ints() == o.expected_commit(coefs, 31337)
     pr = o.open_kzg(f, Fr(u), pk)
     assert (pr.y.sanitize().value, pr.w.affine_ints()) == o.expected_open(coefs, u, 31337)
+
+
+def test_g2_kats_bn128_rs_304_320():
+    """bn128.rs:304-320 (test_g2) and bn128.rs:254-283 (test_fq2) on the oracle's G2 restatement, the
+    public value of 2*G2 (EIP-197 / py_ecc bn128 test vector), and the fast cross-check path."""
+    g = o.generator_g2()
+    assert g.y.mul_ref(g.y) - g.x.mul_ref(g.x).mul_ref(g.x) == o.get_b2()
+    assert g * 2 + g + g == (g * 2) * 2
+    assert g * 9 + g * 5 == g * 12 + g * 2
+    assert (g * o.order()).is_point_at_infinity()
+    assert (g * 2).affine_ints() == (
+        (18029695676650738226693292988307914797657423701064905010927197838374790804409,
+         14583779054894525174450323658765874724019480979794335525732096752006891875705),
+        (2140229616977736810657479771656733941598412651537078903776637920509952744750,
+         11474861747383700316476719153975578001603231366361248090558603872215261634898))
+    # test_fq2
+    x, f = o.Fq2([1, 0]), o.Fq2([1, 2])
+    assert x.add_ref(f) == o.Fq2([2, 2])
+    assert o.Fq2([2, 1]).div_ref(o.Fq2([2, 1])) == o.Fq2.one()
+    assert o.Fq2.one().div_ref(f) + x.div_ref(f) == (o.Fq2.one() + x) / f
+    assert o.Fq2.one() * f + x * f == (o.Fq2.one() + x) * f
+    # u^2 = -1; the fast path agrees with the faithful one; the wire format round-trips
+    assert o.Fq2([0, 1]) * o.Fq2([0, 1]) == o.Fq2([-1])
+    for k in (1, 2, 3, 77, 123456789):
+        assert (g * k).affine_ints() == o.g2_fast_mul(k)
+        assert o.g2_from_bytes(o.g2_to_bytes(o.g2_fast_mul(k))) == o.g2_fast_mul(k)
+    assert o.g2_fast_mul(o.R_MOD) is None and o.g2_from_bytes(bytes(128)) is None
+    pw = o.setup_kzg_g2(g, 5, 3)
+    assert [p.affine_ints() for p in pw] == [o.g2_fast_mul(1), o.g2_fast_mul(5), o.g2_fast_mul(25)]

@@ -131,6 +131,11 @@ int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t
  * cost of the MSM itself - meant for correctness and moderate sizes, not the hot path). */
 int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_or_null /* n*64 */, size_t n,
                  uint8_t out[64]);
+/* G2 MSM sum_i scalars[i] * points[i] with caller-supplied affine G2 points (128 B each, layout as in
+ * myzkp_srs_generate_g2): the accumulate_curve_points call sites over G2 (zksnark/utils.rs:83-93, e.g.
+ * tutorial_snark/protocol_2.rs:68).  One double-and-add per term plus a tree sum - sized for the hundreds of
+ * terms those callers have, not a Pippenger.  n == 0 -> infinity. */
+int myzkp_g2_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points /* n*128 */, size_t n, uint8_t out[128]);
 /* Polynomial::eval (polynomial.rs:120-128). */
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]);
 /* y and the quotient coefficients themselves (n-1 of them; n >= 1). */

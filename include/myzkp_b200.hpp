@@ -74,6 +74,14 @@ inline std::vector<G2Point> powers_2(const PublicKeyKZG& pk, const Scalar& alpha
                                  out.empty() ? nullptr : out[0].xy.data()));
   return out;
 }
+// accumulate_curve_points over G2 (zksnark/utils.rs:83-93): sum_i assignment[i] * g_vec[i]
+inline G2Point accumulate_curve_points(const std::vector<G2Point>& g_vec, const std::vector<Scalar>& assignment,
+                                       const PublicKeyKZG& pk) {
+  const size_t n = g_vec.size() < assignment.size() ? g_vec.size() : assignment.size();  // zip() stops at the shorter
+  G2Point out;
+  pk.check(myzkp_g2_msm(pk.ctx(), n ? assignment[0].data() : nullptr, n ? g_vec[0].xy.data() : nullptr, n, out.xy.data()));
+  return out;
+}
 // commit_kzg (kzg.rs:57-59)
 inline CommitmentKZG commit_kzg(const Polynomial& f, const PublicKeyKZG& pk) {
   G1Point c;

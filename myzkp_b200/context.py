@@ -224,6 +224,17 @@ class Context:
         self._ck(self._lib.myzkp_g1_msm(self.h, _ptr(a), _ptr(pb) if pb is not None else None, a.shape[0], _ptr(out)))
         return point_from_bytes(out)
 
+    def g2_msm(self, scalars, points):
+        """sum_i scalars[i] * points[i] over G2 (accumulate_curve_points, zksnark/utils.rs:83-93); points as
+        ((x.c0, x.c1), (y.c0, y.c1)) tuples / None."""
+        a = scalars_to_bytes(scalars)
+        pb = np.frombuffer(b"".join(g2_to_bytes(p) for p in points), dtype=np.uint8).reshape(-1, 128).copy()
+        if pb.shape[0] != a.shape[0]:
+            raise ValueError("scalars and points differ in length")
+        out = np.zeros(128, np.uint8)
+        self._ck(self._lib.myzkp_g2_msm(self.h, _ptr(a), _ptr(pb), a.shape[0], _ptr(out)))
+        return g2_from_bytes(out)
+
     def fr_eval(self, coefs, u: int) -> int:
         a = scalars_to_bytes(coefs)
         ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()

@@ -97,6 +97,33 @@ MZ_HD void g2_jac_madd(JacG2& acc, const AffineG2& q) {
   acc.x = x3; acc.y = y3; acc.z = z3;
 }
 
+// acc += q (Jacobian + Jacobian, add-2007-bl) with the same case analysis
+MZ_HD void g2_jac_add(JacG2& acc, const JacG2& q) {
+  if (f2_is_zero(q.z)) return;
+  if (f2_is_zero(acc.z)) { acc = q; return; }
+  Fq2 z1z1 = f2_sqr(acc.z);
+  Fq2 z2z2 = f2_sqr(q.z);
+  Fq2 u1 = f2_mul(acc.x, z2z2);
+  Fq2 u2 = f2_mul(q.x, z1z1);
+  Fq2 s1 = f2_mul(f2_mul(acc.y, q.z), z2z2);
+  Fq2 s2 = f2_mul(f2_mul(q.y, acc.z), z1z1);
+  Fq2 h = f2_sub(u2, u1);
+  Fq2 rr = f2_sub(s2, s1);
+  if (f2_is_zero(h)) {
+    if (f2_is_zero(rr)) g2_jac_dbl(acc);
+    else acc = g2_jac_inf();
+    return;
+  }
+  Fq2 i = f2_sqr(f2_dbl(h));
+  Fq2 j = f2_mul(h, i);
+  Fq2 r2 = f2_dbl(rr);
+  Fq2 v = f2_mul(u1, i);
+  Fq2 x3 = f2_sub(f2_sub(f2_sqr(r2), j), f2_dbl(v));
+  Fq2 y3 = f2_sub(f2_mul(r2, f2_sub(v, x3)), f2_dbl(f2_mul(s1, j)));
+  Fq2 z3 = f2_mul(f2_sub(f2_sub(f2_sqr(f2_add(acc.z, q.z)), z1z1), z2z2), h);
+  acc.x = x3; acc.y = y3; acc.z = z3;
+}
+
 MZ_HD AffineG2 g2_jac_to_affine(const JacG2& p) {
   AffineG2 r;
   if (f2_is_zero(p.z)) { r.x = f2_zero(); r.y = f2_zero(); return r; }
@@ -108,7 +135,7 @@ MZ_HD AffineG2 g2_jac_to_affine(const JacG2& p) {
 }
 
 // [k] base, k = 8 raw (non-Montgomery) little-endian limbs, MSB first; k = 0 -> infinity (curve.rs:169-171)
-MZ_HD AffineG2 g2_scalar_mul(const AffineG2& base, const uint32_t* k) {
+MZ_HD JacG2 g2_scalar_mul_jac(const AffineG2& base, const uint32_t* k) {
   JacG2 acc = g2_jac_inf();
   bool started = false;
   for (int limb = 7; limb >= 0; limb--) {
@@ -120,8 +147,8 @@ MZ_HD AffineG2 g2_scalar_mul(const AffineG2& base, const uint32_t* k) {
       }
     }
   }
-  return g2_jac_to_affine(acc);
+  return acc;
 }
+MZ_HD AffineG2 g2_scalar_mul(const AffineG2& base, const uint32_t* k) { return g2_jac_to_affine(g2_scalar_mul_jac(base, k)); }
 
-// BN128::generator_g2() (bn128.rs:190-205), Montgomery form is produced at run time by the caller
 }  // namespace mz

@@ -35,6 +35,7 @@ extern "C" {
     pub fn myzkp_srs_generate_g2(ctx: *mut myzkp_ctx, alpha_le: *const u8, base_or_null: *const u8, first: usize, n: usize,
                                  out: *mut u8) -> c_int;
     pub fn myzkp_srs_len(ctx: *const myzkp_ctx) -> usize;
+    pub fn myzkp_g2_msm(ctx: *mut myzkp_ctx, scalars_le: *const u8, points: *const u8, n: usize, out: *mut u8) -> c_int;
 
     pub fn myzkp_kzg_commit(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, out_c: *mut u8) -> c_int;
     pub fn myzkp_kzg_open(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8,

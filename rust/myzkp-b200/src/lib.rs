@@ -129,6 +129,19 @@ pub fn setup_kzg_with_full_g2(g1: &G1Point, g2: &G2Point, max_d: usize) -> GpuPu
     setup(g1, g2, max_d, max_d + 1)
 }
 
+/// accumulate_curve_points over G2 (zksnark/utils.rs:83-93): sum_i assignment[i] * g_vec[i] on the GPU
+pub fn accumulate_curve_points_g2(g_vec: &[G2Point], assignment: &[FqOrder], pk: &GpuPublicKeyKZG) -> G2Point {
+    let n = g_vec.len().min(assignment.len()); // zip() stops at the shorter slice
+    let scalars = marshal_scalars(&assignment[..n]);
+    let mut pts = Vec::with_capacity(128 * n);
+    for g in &g_vec[..n] {
+        pts.extend_from_slice(&g2_to_bytes(g));
+    }
+    let mut out = [0u8; 128];
+    check(pk.ctx, unsafe { sys::myzkp_g2_msm(pk.ctx, scalars.as_ptr(), pts.as_ptr(), n, out.as_mut_ptr()) });
+    g2_from_bytes(&out)
+}
+
 /// commit_kzg (kzg.rs:57-59)
 pub fn commit_kzg(f: &Polynomial<FqOrder>, pk: &GpuPublicKeyKZG) -> CommitmentKZG {
     let bytes = marshal_scalars(&f.coef);

@@ -25,6 +25,16 @@ void emul_g2_add(const uint32_t* p, const uint32_t* q, uint32_t* out) {
   AffineG2 r = g2_jac_to_affine(acc);
   store_raw(r.x.c0, out); store_raw(r.x.c1, out + 8); store_raw(r.y.c0, out + 16); store_raw(r.y.c1, out + 24);
 }
+// [k1] p + [k2] q through the Jacobian + Jacobian addition (k = 0 gives infinity operands)
+void emul_g2_lincomb(const uint32_t* p, const uint32_t* k1, const uint32_t* q, const uint32_t* k2, uint32_t* out) {
+  AffineG2 a, b;
+  a.x.c0 = load_mont(p); a.x.c1 = load_mont(p + 8); a.y.c0 = load_mont(p + 16); a.y.c1 = load_mont(p + 24);
+  b.x.c0 = load_mont(q); b.x.c1 = load_mont(q + 8); b.y.c0 = load_mont(q + 16); b.y.c1 = load_mont(q + 24);
+  JacG2 x = g2_scalar_mul_jac(a, k1), y = g2_scalar_mul_jac(b, k2);
+  g2_jac_add(x, y);
+  AffineG2 r = g2_jac_to_affine(x);
+  store_raw(r.x.c0, out); store_raw(r.x.c1, out + 8); store_raw(r.y.c0, out + 16); store_raw(r.y.c1, out + 24);
+}
 void emul_fq2_inv(const uint32_t* a, uint32_t* out) {
   Fq2 x; x.c0 = load_mont(a); x.c1 = load_mont(a + 8);
   Fq2 r = f2_inv(x);

@@ -57,7 +57,21 @@ def main():
         gem.append({"name": name, "alpha": str(alpha), "coefs": [str(x) for x in coefs], "rhos": [str(x) for x in rhos],
                     "folds": [[str(v) for v in p.canonical()] for p in fs], "commitments": [pt(p) for p in cm]})
         print(name, "done", file=sys.stderr)
-    out = {"generator": "tests/golden/gen_golden.py (faithful oracle path)", "kzg": cases, "gemini": gem}
+    # G2 half of the public key (kzg.rs:37, 47-52) with the reference's affine law over Fq2
+    def pt2(p):
+        t = p.affine_ints()
+        return None if t is None else [[str(t[0][0]), str(t[0][1])], [str(t[1][0]), str(t[1][1])]]
+
+    g2 = o.generator_g2()
+    g2s = []
+    other = g2.mul_ref(0xABCDEF)
+    for name, alpha, n, base in [("setup_kzg_alpha_123456789", 123456789, 2, g2),
+                                 ("full_g2_random_alpha", rnd.randrange(o.R_MOD), 5, g2),
+                                 ("other_base", rnd.randrange(o.R_MOD), 3, other),
+                                 ("alpha_zero", 0, 3, g2)]:
+        g2s.append({"name": name, "alpha": str(alpha), "base": pt2(base), "powers_2": [pt2(p) for p in o.setup_kzg_g2(base, alpha, n)]})
+        print(name, "done", file=sys.stderr)
+    out = {"generator": "tests/golden/gen_golden.py (faithful oracle path)", "kzg": cases, "gemini": gem, "g2": g2s}
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_golden.json"), "w") as fh:
         json.dump(out, fh, indent=1)
 

@@ -216,6 +216,13 @@ def test_g2_group_law_emulated():
             out = A32()
             L.emul_g2_add(enc(a), enc(b), out)
             assert dec(out) == o._g2_fast_add(a, b)
+    # Jacobian + Jacobian: generic, P + P, P + (-P), infinity on either side
+    h = o.g2_fast_mul(777)
+    for k1, pa, k2, pb in [(5, gen, 9, h), (3, gen, 3, gen), (4, gen, R - 4, gen), (0, gen, 6, h), (6, h, 0, gen), (0, gen, 0, h),
+                           (rnd.randrange(R), gen, rnd.randrange(R), h)]:
+        out = A32()
+        L.emul_g2_lincomb(enc(pa), tl(k1), enc(pb), tl(k2), out)
+        assert dec(out) == o._g2_fast_add(o.g2_fast_mul(k1, pa), o.g2_fast_mul(k2, pb)), (k1, k2)
     for _ in range(20):
         x = (rnd.randrange(P), rnd.randrange(P))
         out = (ctypes.c_uint32 * 16)()

@@ -29,3 +29,14 @@ def test_golden_gemini_matches_fold_ints():
         assert [[int(v) for v in f] for f in case["folds"]] == folds
         for f, c in zip(folds, case["commitments"]):
             assert o.expected_commit(f, alpha) == _pt(c)
+
+
+def _pt2(p):
+    return None if p is None else ((int(p[0][0]), int(p[0][1])), (int(p[1][0]), int(p[1][1])))
+
+
+def test_golden_g2_matches_fast_path():
+    for case in G["g2"]:
+        alpha, base = int(case["alpha"]), _pt2(case["base"])
+        for i, p in enumerate(case["powers_2"]):
+            assert o.g2_fast_mul(pow(alpha, i, o.R_MOD), base) == _pt2(p), case["name"]

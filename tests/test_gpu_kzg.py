@@ -529,6 +529,12 @@ def test_g2_powers_of_the_public_key(ctx):
     assert len(pk) == 41 and len(pk.powers_2) == 41
     for i, p in enumerate(pk.powers_2):
         assert p.as_tuple() == o.g2_fast_mul(pow(alpha, i, R)), i
+    # committed golden vectors (faithful oracle path)
+    for case in G["g2"]:
+        base = tuple(tuple(int(v) for v in c) for c in case["base"])
+        got = ctx.srs_generate_g2(int(case["alpha"]), len(case["powers_2"]), 0, base)
+        exp = [None if p is None else tuple(tuple(int(v) for v in c) for c in p) for p in case["powers_2"]]
+        assert got == exp, case["name"]
     # window into the powers, an arbitrary base point, a small alpha against the faithful oracle
     base = o.g2_fast_mul(0xABCDEF)
     got = ctx.srs_generate_g2(3, 5, first=2, base=base)
@@ -548,6 +554,30 @@ def test_g2_powers_of_the_public_key(ctx):
     code = ctx._lib.myzkp_srs_generate_g2(ctx.h, a.ctypes.data_as(ctypes.c_void_p), bad.ctypes.data_as(ctypes.c_void_p), 0, 1,
                                           out.ctypes.data_as(ctypes.c_void_p))
     assert code != 0
+
+
+def test_g2_msm_with_caller_points(ctx):
+    """accumulate_curve_points over G2 (zksnark/utils.rs:83-93; e.g. g2_r in tutorial_snark/protocol_2.rs:68):
+    fold of acc + g * a over caller-supplied G2 points, vs the oracle."""
+    rnd = random.Random(21)
+    for n in (0, 1, 2, 63, 64, 65, 300):
+        ks = [rnd.randrange(1, R) for _ in range(n)]
+        pts = [o.g2_fast_mul(k) for k in ks]
+        sc = [rnd.choice([0, 1, R - 1, rnd.randrange(R)]) for _ in range(n)]
+        if n >= 2:
+            pts[1] = None  # infinity among the points
+        exp = o.g2_fast_mul(sum(s * k for s, k, p in zip(sc, ks, pts) if p is not None) % R)
+        assert ctx.g2_msm(sc, pts) == exp, n
+    # duplicates and opposite points cancel; the faithful affine law on a tiny case
+    g = (o.G2_GEN_X, o.G2_GEN_Y)
+    neg = (g[0], ((-g[1][0]) % o.P_MOD, (-g[1][1]) % o.P_MOD))
+    assert ctx.g2_msm([5, 5], [g, neg]) is None
+    assert ctx.g2_msm([3, 3], [g, g]) == o.g2_fast_mul(6)
+    G2 = o.generator_g2()
+    acc = o.G2Point.point_at_infinity()
+    for a, k in [(7, 2), (11, 3)]:
+        acc = acc + (G2 * k) * a
+    assert ctx.g2_msm([7, 11], [o.g2_fast_mul(2), o.g2_fast_mul(3)]) == acc.affine_ints()
 
 
 def test_cpp_host_through_header_mirror():

@@ -136,6 +136,15 @@ int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* point
  * tutorial_snark/protocol_2.rs:68).  One double-and-add per term plus a tree sum - sized for the hundreds of
  * terms those callers have, not a Pippenger.  n == 0 -> infinity. */
 int myzkp_g2_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points /* n*128 */, size_t n, uint8_t out[128]);
+/* Optimal ate pairings e(g1[i], g2[i]) - optimal_ate_pairing, curve/bn128.rs:147-181 - one warp each.
+ * out[i] = the Fq12 value as the reference represents it: 12 coefficients of w^k in Fq[w]/(w^12 - 18 w^6 + 82),
+ * 32 B little-endian canonical each (384 B per pairing); a point at infinity on either side gives 1. */
+int myzkp_pairing(myzkp_ctx* ctx, const uint8_t* g1 /* n*64 */, const uint8_t* g2 /* n*128 */, size_t n, uint8_t* out /* n*384 */);
+/* *out_is_one = (prod_i e(g1[i], g2[i]) == 1): n Miller loops side by side, ONE final exponentiation.
+ * The pairing equations of verify_kzg (kzg.rs:90-102), batch_verify_kzg (kzg.rs:104-119) and
+ * verify_degree_bound (kzg.rs:136-144) are such products after moving one side over with a negated point. */
+int myzkp_pairing_product_is_one(myzkp_ctx* ctx, const uint8_t* g1 /* n*64 */, const uint8_t* g2 /* n*128 */, size_t n,
+                                 int* out_is_one);
 /* Polynomial::eval (polynomial.rs:120-128). */
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]);
 /* y and the quotient coefficients themselves (n-1 of them; n >= 1). */

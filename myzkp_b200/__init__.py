@@ -9,5 +9,6 @@ from .context import Context, R_MOD, P_MOD  # noqa: F401
 from .kzg import (  # noqa: F401
     BN128, BatchProofKZG, CommitmentKZG, G1Point, G2Point, Polynomial, ProofDegreeBound, ProofKZG, PublicKeyKZG,
     batch_open_kzg, commit_kzg, open_kzg, prove_degree_bound, setup_kzg, setup_kzg_with_full_g2,
+    batch_verify_kzg, optimal_ate_pairing, verify_degree_bound, verify_kzg,
 )
-from .gemini import ProofGemini, SplitFoldError, commit_gemini, open_gemini, split_and_fold_commit  # noqa: F401
+from .gemini import ProofGemini, SplitFoldError, commit_gemini, open_gemini, split_and_fold_commit, verify_gemini  # noqa: F401

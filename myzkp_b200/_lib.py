@@ -36,6 +36,8 @@ SIGNATURES = {
     "myzkp_srs_read_g1": (_i, [_vp, _sz, _sz, _vp]),
     "myzkp_srs_generate_g2": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "myzkp_g2_msm": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "myzkp_pairing": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "myzkp_pairing_product_is_one": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "myzkp_srs_len": (_sz, [_vp]),
     "myzkp_kzg_commit": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_kzg_open": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),

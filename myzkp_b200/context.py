@@ -235,6 +235,28 @@ class Context:
         self._ck(self._lib.myzkp_g2_msm(self.h, _ptr(a), _ptr(pb), a.shape[0], _ptr(out)))
         return g2_from_bytes(out)
 
+    def pairing(self, g1_points, g2_points):
+        """[e(P_i, Q_i)] (optimal_ate_pairing, bn128.rs:147-181), each as the 12 Fq coefficients of w^k."""
+        n = len(g1_points)
+        if len(g2_points) != n:
+            raise ValueError("g1 and g2 point lists differ in length")
+        a = np.frombuffer(b"".join(point_to_bytes(p) for p in g1_points), dtype=np.uint8).copy()
+        b = np.frombuffer(b"".join(g2_to_bytes(p) for p in g2_points), dtype=np.uint8).copy()
+        out = np.zeros((n, 12, 32), np.uint8)
+        self._ck(self._lib.myzkp_pairing(self.h, _ptr(a), _ptr(b), n, _ptr(out)))
+        return [[bytes_to_int(out[i, k]) for k in range(12)] for i in range(n)]
+
+    def pairing_product_is_one(self, g1_points, g2_points) -> bool:
+        """prod_i e(P_i, Q_i) == 1 with one final exponentiation."""
+        n = len(g1_points)
+        if len(g2_points) != n:
+            raise ValueError("g1 and g2 point lists differ in length")
+        a = np.frombuffer(b"".join(point_to_bytes(p) for p in g1_points), dtype=np.uint8).copy()
+        b = np.frombuffer(b"".join(g2_to_bytes(p) for p in g2_points), dtype=np.uint8).copy()
+        res = ctypes.c_int(0)
+        self._ck(self._lib.myzkp_pairing_product_is_one(self.h, _ptr(a), _ptr(b), n, ctypes.byref(res)))
+        return bool(res.value)
+
     def fr_eval(self, coefs, u: int) -> int:
         a = scalars_to_bytes(coefs)
         ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()

@@ -6,7 +6,8 @@ from typing import List, Sequence
 import numpy as np
 
 from .context import R_MOD, bytes_to_int
-from .kzg import BatchProofKZG, G1Point, Polynomial, PublicKeyKZG, batch_open_kzg, prove_degree_bound
+from .kzg import (BatchProofKZG, G1Point, Polynomial, PublicKeyKZG, batch_open_kzg, batch_verify_kzg, prove_degree_bound,
+                  verify_degree_bound)
 
 
 class SplitFoldError(ValueError):
@@ -61,3 +62,23 @@ def open_gemini(polys: Sequence[Polynomial], beta: int, pk: PublicKeyKZG) -> Pro
     es = [batch_open_kzg(p, us, pk) for p in polys[: num_polys - 1]]
     degree_proofs = [prove_degree_bound(p, pk, 2 ** (num_polys - i - 1)) for i, p in enumerate(polys)]
     return ProofGemini(es, degree_proofs)
+
+
+def verify_gemini(rhos: Sequence[int], mu: int, beta: int, commitment: Sequence[G1Point], proof: ProofGemini,
+                  pk: PublicKeyKZG) -> bool:
+    """gemini.rs:146-203: degree bounds of every fold, the three-point openings, then the folding identity
+    2 beta e_hat_j == beta (e_j + e_neg_j) + rho_j (e_j - e_neg_j)."""
+    log2_n = len(rhos)
+    if log2_n != len(commitment) - 1:
+        return False
+    if not all(verify_degree_bound(c, p, pk, 2 ** (log2_n - i)) for i, (c, p) in enumerate(zip(commitment, proof.degree_proofs))):
+        return False
+    beta = int(beta) % R_MOD
+    us = [beta, (-beta) % R_MOD, beta * beta % R_MOD]
+    if not all(batch_verify_kzg(us, c, p, pk) for c, p in zip(commitment[:-1], proof.es)):
+        return False
+    es = [p.ys[0] for p in proof.es]
+    es_neg = [p.ys[1] for p in proof.es]
+    es_hat = [p.ys[2] for p in proof.es][1:] + [int(mu) % R_MOD]
+    return all((2 * beta * es_hat[j]) % R_MOD == (beta * (es[j] + es_neg[j]) + int(rhos[j]) * (es[j] - es_neg[j])) % R_MOD
+               for j in range(log2_n))

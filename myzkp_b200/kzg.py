@@ -207,3 +207,72 @@ def batch_open_kzg(f: Polynomial, us: Sequence[int], pk: PublicKeyKZG) -> BatchP
 def prove_degree_bound(f: Polynomial, pk: PublicKeyKZG, d: int) -> ProofDegreeBound:
     """kzg.rs:121-134."""
     return G1Point._from_tuple(pk.ctx.prove_degree_bound(f._wire(), d))
+
+
+def _neg_g1(t):
+    return None if t is None else (t[0], (-t[1]) % P_MOD)
+
+
+def verify_kzg(u: int, c: CommitmentKZG, proof: ProofKZG, pk: PublicKeyKZG) -> bool:
+    """kzg.rs:90-102: e(C, g2) == e(W, [alpha]g2 - [u]g2) * e(g1, g2)^y, checked on the GPU as
+    e(C, g2) * e(-W, [alpha - u]g2) * e([-y]g1, g2) == 1 (three Miller loops, one final exponentiation)."""
+    ctx = pk.ctx
+    u, y = int(u) % R_MOD, int(proof.y) % R_MOD
+    g1 = ctx.srs_read(0, 1)[0]
+    g2, g2_alpha = pk.powers_2[0].as_tuple(), pk.powers_2[1].as_tuple()
+    g2_alpha_minus_u = ctx.g2_msm([1, (-u) % R_MOD], [g2_alpha, g2])
+    g1_minus_y = ctx.g1_msm([(-y) % R_MOD], [g1])
+    return ctx.pairing_product_is_one([c.as_tuple(), _neg_g1(proof.w.as_tuple()), g1_minus_y], [g2, g2_alpha_minus_u, g2])
+
+
+def _interpolate(xs, ys):
+    """Polynomial::interpolate (polynomial.rs:177-200) on k (= a handful of) points: Lagrange form, ints mod r."""
+    k = len(xs)
+    out = [0] * k
+    for i in range(k):
+        num, den = [1], 1
+        for j in range(k):
+            if j != i:
+                num = [(a - xs[j] * b) % R_MOD for a, b in zip([0] + num, num + [0])]
+                den = den * (xs[i] - xs[j]) % R_MOD
+        scale = ys[i] * pow(den, -1, R_MOD) % R_MOD
+        for t in range(len(num)):
+            out[t] = (out[t] + scale * num[t]) % R_MOD
+    return out
+
+
+def _from_monomials(us):
+    """Polynomial::from_monomials (polynomial.rs:202-212): prod (x - u_i)."""
+    z = [1]
+    for u in us:
+        z = [(a - u * b) % R_MOD for a, b in zip([0] + z, z + [0])]
+    return z
+
+
+def batch_verify_kzg(us: Sequence[int], c: CommitmentKZG, proof: BatchProofKZG, pk: PublicKeyKZG) -> bool:
+    """kzg.rs:104-119: e(W, [Z(alpha)]g2) == e(C - [I(alpha)]g1, g2) with I the interpolant of (us, ys) and
+    Z = prod (x - u_i); needs len(us) + 1 powers of g2 (setup_kzg_with_full_g2 for more than one point)."""
+    ctx = pk.ctx
+    us = [int(u) % R_MOD for u in us]
+    ip = _interpolate(us, [int(y) % R_MOD for y in proof.ys])
+    z = _from_monomials(us)
+    if len(z) > len(pk.powers_2):
+        raise ValueError("batch_verify_kzg needs len(us) + 1 powers of g2 (reference: index panic, polynomial.rs:162)")
+    g1_ip = ctx.commit(ip)
+    g2_z = ctx.g2_msm(z, [p.as_tuple() for p in pk.powers_2[: len(z)]])
+    lhs = ctx.g1_msm([1, R_MOD - 1], [c.as_tuple(), g1_ip])  # C - [I(alpha)]g1
+    return ctx.pairing_product_is_one([proof.w.as_tuple(), _neg_g1(lhs)], [g2_z, pk.powers_2[0].as_tuple()])
+
+
+def verify_degree_bound(c: CommitmentKZG, proof: ProofDegreeBound, pk: PublicKeyKZG, d: int) -> bool:
+    """kzg.rs:136-144: e(proof, g2) == e(C, [alpha^(max_d - d)]g2); needs setup_kzg_with_full_g2."""
+    max_d = len(pk) - 1
+    if not 0 <= max_d - d < len(pk.powers_2):
+        raise ValueError("verify_degree_bound needs powers_2[max_d - d] (reference: index panic)")
+    return pk.ctx.pairing_product_is_one([proof.as_tuple(), _neg_g1(c.as_tuple())],
+                                         [pk.powers_2[0].as_tuple(), pk.powers_2[max_d - d].as_tuple()])
+
+
+def optimal_ate_pairing(p: G1Point, q: G2Point, pk: PublicKeyKZG) -> List[int]:
+    """curve/bn128.rs:147-181 on the GPU: the Fq12 value as its 12 coefficients of w^k."""
+    return pk.ctx.pairing([p.as_tuple()], [q.as_tuple()])[0]

@@ -712,6 +712,189 @@ def setup_kzg_g2(g2: G2Point, alpha: int, n: int) -> List[G2Point]:
     return out
 
 
+# --- pairing: Fq12 = Fq[w] / (w^12 - 18 w^6 + 82), G12 points, Miller loop -------------------
+FQ12_MODULUS = [82, 0, 0, 0, 0, 0, -18 % P_MOD, 0, 0, 0, 0, 0, 1]  # bn128.rs:55-72
+ATE_LOOP_COUNT = 29793968203157093288  # bn128.rs:26
+
+
+class Fq12:
+    """ExtendedFieldElement<BN128Modulus, Fq12Poly> (bn128.rs:51-80, efield.rs): polynomial over Fq modulo
+    w^12 - 18 w^6 + 82; `c` = 12 canonical ints, low -> high."""
+
+    __slots__ = ("c",)
+
+    def __init__(self, c: Sequence[int]):
+        _, r = _pdivmod([int(v) % P_MOD for v in c], FQ12_MODULUS)  # efield.rs:103-108
+        self.c = (r + [0] * 12)[:12]
+
+    @classmethod
+    def from_value(cls, v: int) -> "Fq12":
+        return cls([v])
+
+    @classmethod
+    def zero(cls):
+        return cls([0])
+
+    @classmethod
+    def one(cls):
+        return cls([1])
+
+    def is_zero(self) -> bool:
+        return not any(self.c)
+
+    def add_ref(self, o):
+        return Fq12([a + b for a, b in zip(self.c, o.c)])
+
+    def sub_ref(self, o):
+        return Fq12([a - b for a, b in zip(self.c, o.c)])
+
+    def mul_ref(self, o):  # efield.rs:351-353
+        return Fq12(_pmul(self.c, o.c))
+
+    def inverse(self):
+        """efield.rs:126-151."""
+        lm, hm = [1], [0]
+        low, high = _ptrim(list(self.c)), list(FQ12_MODULUS)
+        while low:
+            q, r = _pdivmod(high, low)
+            nm = _psub(hm, _pmul(lm, q))
+            high, hm, low, lm = low, lm, r, nm
+        inv0 = Fq.from_value(high[0]).inverse().sanitize().value
+        return Fq12([v * inv0 for v in hm])
+
+    def div_ref(self, o):
+        return self.mul_ref(o.inverse())
+
+    def pow(self, n: int):
+        """Square-and-multiply; the result does not depend on the order of the multiplications."""
+        result, base = Fq12.one(), self
+        while n > 0:
+            if n & 1:
+                result = result.mul_ref(base)
+            base = base.mul_ref(base)
+            n >>= 1
+        return result
+
+    def __eq__(self, o):
+        return isinstance(o, Fq12) and self.c == o.c
+
+    def __hash__(self):
+        return hash(tuple(self.c))
+
+    def __add__(self, o):
+        return self.add_ref(o)
+
+    def __sub__(self, o):
+        return self.sub_ref(o)
+
+    def __mul__(self, o):
+        return self.mul_ref(o)
+
+    def __neg__(self):
+        return Fq12([-v for v in self.c])
+
+    def __truediv__(self, o):
+        return self.div_ref(o)
+
+    def sanitize(self):
+        return self
+
+    def __repr__(self):
+        return f"Fq12({self.c})"
+
+
+class G12Point(G1Point):
+    """EllipticCurvePoint<Fq12, BN128Curve> (bn128.rs:81)."""
+
+    __slots__ = ()
+    F = Fq12
+
+
+def cast_g1_to_g12(g: G1Point) -> G12Point:
+    """bn128.rs:83-96."""
+    if g.is_point_at_infinity():
+        return G12Point.point_at_infinity()
+    return G12Point.new(Fq12([g.x.sanitize().value]), Fq12([g.y.sanitize().value]))
+
+
+def twist_g2_to_g12(g: G2Point) -> G12Point:
+    """bn128.rs:98-145: u -> w^6 - 9, then (x w^2, y w^3)."""
+    if g.is_point_at_infinity():
+        return G12Point.point_at_infinity()
+    w = Fq12([0, 1])
+    x, y = g.x.c, g.y.c
+    nx = Fq12([x[0] - 9 * x[1], 0, 0, 0, 0, 0, x[1]])
+    ny = Fq12([y[0] - 9 * y[1], 0, 0, 0, 0, 0, y[1]])
+    return G12Point.new(nx * w.pow(2), ny * w.pow(3))
+
+
+def get_lambda(p, q, r):
+    """curve.rs:285-311: the line through p and q (tangent if equal) over the vertical through p + q, at r."""
+    F = type(p).F
+    if p.is_point_at_infinity() or q.is_point_at_infinity() or r.is_point_at_infinity():
+        return F.one()
+    if (p == q and p.y == F.zero()) or (p != q and p.x == q.x):
+        return r.x.sub_ref(p.x)
+    slope = p.line_slope(q)
+    numerator = r.y.sub_ref(p.y).sub_ref(slope.mul_ref(r.x.sub_ref(p.x)))
+    denominator = r.x.add_ref(p.x).add_ref(q.x).sub_ref(slope.mul_ref(slope))
+    return numerator / denominator
+
+
+def miller(p, q, m: int):
+    """curve.rs:313-339."""
+    F = type(p).F
+    if p.is_point_at_infinity() or q.is_point_at_infinity():
+        return F.one(), type(p).point_at_infinity()
+    if p == q:
+        return F.one(), p.clone()
+    f, t = F.one(), p.clone()
+    for i in reversed(range(m.bit_length() - 1)):
+        f = f.mul_ref(f) * get_lambda(t, t, q)
+        t = t.add_ref(t)
+        if (m >> i) & 1:
+            f = f * get_lambda(t, p, q)
+            t = t.add_ref(p)
+    return f, t
+
+
+FINAL_EXPONENT = (P_MOD ** 12 - 1) // R_MOD
+
+
+def optimal_ate_pairing(p_g1: G1Point, q_g2: G2Point) -> Fq12:
+    """bn128.rs:147-181."""
+    p = cast_g1_to_g12(p_g1)
+    q = twist_g2_to_g12(q_g2)
+    if p.is_point_at_infinity() or q.is_point_at_infinity():
+        return Fq12.one()
+    f = Fq12.one()
+    if p != q:
+        f, r = miller(q, p, ATE_LOOP_COUNT)
+        q1 = G12Point.new(q.x.pow(P_MOD), q.y.pow(P_MOD))
+        nq2 = G12Point.new(q1.x.pow(P_MOD), -q1.y.pow(P_MOD))
+        f = f * get_lambda(r, q1, p)
+        r = r.add_ref(q1)
+        f = f * get_lambda(r, nq2, p)
+    return f.pow(FINAL_EXPONENT)
+
+
+def verify_kzg(u: Fr, c: G1Point, proof: "ProofKZG", powers_1: Sequence[G1Point], powers_2: Sequence[G2Point]) -> bool:
+    """kzg.rs:90-102."""
+    g1, g2, g2_alpha = powers_1[0], powers_2[0], powers_2[1]
+    g2_u = g2.mul_ref(u.sanitize().get_value())
+    g2_alpha_minus_u = g2_alpha - g2_u
+    e1 = optimal_ate_pairing(proof.w, g2_alpha_minus_u)
+    e2 = optimal_ate_pairing(g1, g2)
+    e3 = optimal_ate_pairing(c, g2)
+    return e3 == e1 * e2.pow(proof.y.sanitize().get_value())
+
+
+def verify_degree_bound(c: G1Point, proof: G1Point, powers_1: Sequence[G1Point], powers_2: Sequence[G2Point], d: int) -> bool:
+    """kzg.rs:136-144 (needs setup_kzg_with_full_g2)."""
+    max_d = len(powers_1) - 1
+    return optimal_ate_pairing(proof, powers_2[0]) == optimal_ate_pairing(c, powers_2[max_d - d])
+
+
 # fast independent path for G2 (Jacobian over Fq2 as int pairs) - used for larger checks
 def _f2mul(a, b):
     return ((a[0] * b[0] - a[1] * b[1]) % P_MOD, (a[0] * b[1] + a[1] * b[0]) % P_MOD)

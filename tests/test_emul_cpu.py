@@ -19,7 +19,7 @@ RR = 1 << 256
 def _build(name):
     src = os.path.join(HERE, "emul", f"{name}.cpp")
     out = os.path.join(HERE, "emul", f"lib{name}.so")
-    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh", "g2.cuh")]
+    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh", "g2.cuh", "pairing.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)
@@ -228,3 +228,48 @@ def test_g2_group_law_emulated():
         out = (ctypes.c_uint32 * 16)()
         L.emul_fq2_inv((ctypes.c_uint32 * 16)(*[(v >> (32 * i)) & 0xFFFFFFFF for v in x for i in range(8)]), out)
         assert (fl(out), fl(out, 8)) == tuple((o.Fq2(list(x)).inverse()).c)
+
+
+def test_pairing_emulated():
+    """csrc/pairing.cuh (Fq12 product spread over lanes, twist-side Miller loop, final exponentiation) against the
+    oracle's restatement of the reference's optimal_ate_pairing (bn128.rs:147-181): identical Fq12 VALUES."""
+    L = _build("emul_pairing")
+    rnd = random.Random(5)
+    A96 = ctypes.c_uint32 * 96
+
+    def enc12(c):
+        return A96(*[(v >> (32 * i)) & 0xFFFFFFFF for v in c for i in range(8)])
+
+    def dec12(a):
+        return [fl(a, 8 * k) for k in range(12)]
+
+    for _ in range(6):
+        x = [rnd.randrange(P) for _ in range(12)]
+        y = [rnd.randrange(P) for _ in range(12)] if rnd.random() < 0.7 else [rnd.choice([0, 1, P - 1]) for _ in range(12)]
+        out = A96()
+        L.emul_f12_mul(enc12(x), enc12(y), out)
+        assert dec12(out) == (o.Fq12(x) * o.Fq12(y)).c
+
+    def enc1(pt):
+        vals = [0, 0] if pt is None else list(pt)
+        return (ctypes.c_uint32 * 16)(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vals for i in range(8)])
+
+    def enc2(pt):
+        vals = [0, 0, 0, 0] if pt is None else [pt[0][0], pt[0][1], pt[1][0], pt[1][1]]
+        return (ctypes.c_uint32 * 32)(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vals for i in range(8)])
+
+    def pairing(p1, p2):
+        out = A96()
+        L.emul_pairing(enc1(p1), enc2(p2), 1, out)
+        return dec12(out)
+
+    def oracle_pairing(k1, k2):
+        return o.optimal_ate_pairing(o.generator_g1().mul_ref(k1), o.generator_g2().mul_ref(k2)).c
+
+    one = [1] + [0] * 11
+    assert pairing(o.fast_mul(1), o.g2_fast_mul(1)) == oracle_pairing(1, 1)
+    assert pairing(o.fast_mul(37), o.g2_fast_mul(27)) == oracle_pairing(999, 1)  # bn128.rs:362-364
+    assert pairing(None, o.g2_fast_mul(3)) == one and pairing(o.fast_mul(3), None) == one
+    e1 = o.Fq12(pairing(o.fast_mul(1), o.g2_fast_mul(1)))
+    neg = o.fast_mul(R - 1)
+    assert (e1 * o.Fq12(pairing(neg, o.g2_fast_mul(1)))).c == one  # bn128.rs:345-347

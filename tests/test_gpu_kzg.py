@@ -580,6 +580,69 @@ def test_g2_msm_with_caller_points(ctx):
     assert ctx.g2_msm([7, 11], [o.g2_fast_mul(2), o.g2_fast_mul(3)]) == acc.affine_ints()
 
 
+def test_pairing_values_match_the_reference_algorithm(ctx):
+    """myzkp_pairing vs the oracle's restatement of optimal_ate_pairing (bn128.rs:147-181): identical Fq12
+    coefficients; plus the identities of bn128.rs:341-365 (test_pairing) on the device values."""
+    g1, g2 = o.generator_g1(), o.generator_g2()
+    P1, Q1 = o.fast_mul(1), o.g2_fast_mul(1)
+    vals = ctx.pairing([P1, o.fast_mul(R - 1), o.fast_mul(2), P1, o.fast_mul(37), o.fast_mul(999), None, P1],
+                       [Q1, Q1, Q1, o.g2_fast_mul(2), o.g2_fast_mul(27), Q1, Q1, None])
+    p1, pn1, p2, po2, p3, po3, inf_a, inf_b = [o.Fq12(v) for v in vals]
+    assert p1 == o.optimal_ate_pairing(g1, g2)
+    assert p3 == o.optimal_ate_pairing(g1.mul_ref(37), g2.mul_ref(27))
+    assert p1 * pn1 == o.Fq12.one() and p1 * p1 == p2 and p1 * p1 == po2 and p3 == po3
+    assert p1 != p2 and p1 != pn1 and inf_a == o.Fq12.one() and inf_b == o.Fq12.one()
+    assert ctx.pairing_product_is_one([P1, o.fast_mul(R - 1)], [Q1, Q1])
+    assert not ctx.pairing_product_is_one([P1, P1], [Q1, Q1])
+    assert ctx.pairing_product_is_one([], [])
+
+
+def test_verify_kzg_batch_degree_bound_and_gemini(ctx):
+    """The reference's own protocol tests, end to end on the device: test_kzg (kzg.rs:152-175), test_batch_kzg
+    (:177-205), test_degree_bound (:207-233) and test_gemini (gemini.rs:288-328); verify_kzg's boolean also
+    against the oracle's restatement (three reference pairings)."""
+    g1, g2 = mz.BN128.generator_g1(), mz.BN128.generator_g2()
+    alpha = 123456789
+    f = mz.Polynomial([6, 11, 6, 1])  # from_monomials([-1, -2, -3])
+    pk = mz.setup_kzg(g1, g2, 3, alpha=alpha, ctx=ctx)
+    c = mz.commit_kzg(f, pk)
+    proof = mz.open_kzg(f, 5, pk)
+    assert mz.verify_kzg(5, c, proof, pk)
+    assert not mz.verify_kzg(6, c, proof, pk)
+    assert not mz.verify_kzg(5, c, mz.ProofKZG(proof.y + 1, proof.w), pk)
+    assert not mz.verify_kzg(5, mz.commit_kzg(mz.Polynomial([6, 11, 6, 2]), pk), proof, pk)
+    opk = o.setup_kzg(o.generator_g1(), 3, alpha)
+    op2 = o.setup_kzg_g2(o.generator_g2(), alpha, 2)
+    oproof = o.open_kzg(o.Polynomial([Fr(v) for v in [6, 11, 6, 1]]), Fr(5), opk)
+    oc = o.commit_kzg(o.Polynomial([Fr(v) for v in [6, 11, 6, 1]]), opk)
+    assert o.verify_kzg(Fr(5), oc, oproof, opk.powers_1, op2) is True
+    assert o.verify_kzg(Fr(6), oc, oproof, opk.powers_1, op2) is False
+    # test_batch_kzg
+    pk = mz.setup_kzg_with_full_g2(g1, g2, 3, alpha=alpha, ctx=ctx)
+    c = mz.commit_kzg(f, pk)
+    zs = [5, 7]
+    bp = mz.batch_open_kzg(f, zs, pk)
+    assert mz.batch_verify_kzg(zs, c, bp, pk)
+    bp.ys[0] = (bp.ys[0] + 1) % R
+    assert not mz.batch_verify_kzg(zs, c, bp, pk)
+    # test_degree_bound: deg f = 3 is bounded by 3, and a proof for d = 3 does not verify for d = 2
+    dp = mz.prove_degree_bound(f, pk, 3)
+    assert mz.verify_degree_bound(c, dp, pk, 3)
+    assert not mz.verify_degree_bound(c, dp, pk, 2)
+    pk4 = mz.setup_kzg_with_full_g2(g1, g2, 4, alpha=alpha, ctx=ctx)  # the reference's case: max_d = 4, d = 3
+    assert mz.verify_degree_bound(mz.commit_kzg(f, pk4), mz.prove_degree_bound(f, pk4, 3), pk4, 3)
+    # test_gemini
+    pk = mz.setup_kzg_with_full_g2(g1, g2, 8, alpha=synth.random_scalar(synth.SEED_ALPHA), ctx=ctx)
+    coef, rhos = list(range(1, 9)), [2, 3, 4]
+    cms, polys = mz.split_and_fold_commit(coef, rhos, pk, want_folds=True)
+    fs = [mz.Polynomial(coef)] + polys
+    mu = 382  # gemini.rs:294-307: sum coef_i * tensor(rhos)_i
+    assert fs[-1]._wire() == [mu]
+    gp = mz.open_gemini(fs, 1234, pk)
+    assert mz.verify_gemini(rhos, mu, 1234, cms, gp, pk)
+    assert not mz.verify_gemini(rhos, mu + 1, 1234, cms, gp, pk)
+
+
 def test_cpp_host_through_header_mirror():
     """tests/cpp/abi_smoke.cpp: a C++ host over include/myzkp_b200.hpp reproduces the test_kzg anchor."""
     import subprocess

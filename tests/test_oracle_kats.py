@@ -144,3 +144,31 @@ def test_g2_kats_bn128_rs_304_320():
     assert o.g2_fast_mul(o.R_MOD) is None and o.g2_from_bytes(bytes(128)) is None
     pw = o.setup_kzg_g2(g, 5, 3)
     assert [p.affine_ints() for p in pw] == [o.g2_fast_mul(1), o.g2_fast_mul(5), o.g2_fast_mul(25)]
+
+
+def test_pairing_kats_bn128_rs_341_365():
+    """bn128.rs:341-365 (test_pairing) and bn128.rs:322-339 (test_g12) on the oracle's restatement of
+    optimal_ate_pairing / miller / get_lambda, and kzg.rs:152-175 (test_kzg) through its verify_kzg."""
+    g1, g2 = o.generator_g1(), o.generator_g2()
+    one = o.Fq12.one()
+    p1 = o.optimal_ate_pairing(g1, g2)
+    pn1 = o.optimal_ate_pairing(-g1, g2)
+    assert p1 * pn1 == one
+    np1 = o.optimal_ate_pairing(g1, -g2)
+    assert p1 * np1 == one and pn1 == np1
+    p2 = o.optimal_ate_pairing(g1.mul_ref(2), g2)
+    assert p1 * p1 == p2 and p1 != p2 and p1 != np1 and p2 != np1
+    assert p1 * p1 == o.optimal_ate_pairing(g1, g2.mul_ref(2))
+    assert o.optimal_ate_pairing(g1.mul_ref(37), g2.mul_ref(27)) == o.optimal_ate_pairing(g1.mul_ref(999), g2)
+    # test_g12: the twisted generator lies on y^2 = x^3 + 3 over Fq12
+    g12 = o.twist_g2_to_g12(g2)
+    g12_9 = g12.mul_ref(9)
+    assert g12_9.y.pow(2) - g12_9.x.pow(3) == o.Fq12([3])
+    assert g12.mul_ref(2) + g12 + g12 == g12.mul_ref(2).mul_ref(2)
+    # test_kzg with a fixed alpha
+    alpha = 123456789
+    pk = o.setup_kzg(g1, 3, alpha)
+    p2s = o.setup_kzg_g2(g2, alpha, 2)
+    f = o.Polynomial([o.Fr(v) for v in [6, 11, 6, 1]])
+    c, proof = o.commit_kzg(f, pk), o.open_kzg(f, o.Fr(5), pk)
+    assert o.verify_kzg(o.Fr(5), c, proof, pk.powers_1, p2s)

@@ -82,6 +82,23 @@ inline G2Point accumulate_curve_points(const std::vector<G2Point>& g_vec, const 
   pk.check(myzkp_g2_msm(pk.ctx(), n ? assignment[0].data() : nullptr, n ? g_vec[0].xy.data() : nullptr, n, out.xy.data()));
   return out;
 }
+// prod_i e(g1[i], g2[i]) == 1 (optimal_ate_pairing, curve/bn128.rs:147-181; one final exponentiation)
+inline bool pairing_product_is_one(const std::vector<G1Point>& g1, const std::vector<G2Point>& g2, const PublicKeyKZG& pk) {
+  const size_t n = g1.size() < g2.size() ? g1.size() : g2.size();
+  int ok = 0;
+  pk.check(myzkp_pairing_product_is_one(pk.ctx(), n ? g1[0].xy.data() : nullptr, n ? g2[0].xy.data() : nullptr, n, &ok));
+  return ok != 0;
+}
+// verify_degree_bound (kzg.rs:136-144): e(proof, g2) == e(c, [alpha^(max_d - d)]g2), with c negated by the caller's
+// field arithmetic replaced by a G1 MSM with scalar r - 1
+inline bool verify_degree_bound(const CommitmentKZG& c, const G1Point& proof, const PublicKeyKZG& pk, const G2Point& g2,
+                                const G2Point& g2_pow_maxd_minus_d) {
+  Scalar minus_one = {0x00, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                      0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};  // r - 1
+  G1Point neg_c;
+  pk.check(myzkp_g1_msm(pk.ctx(), minus_one.data(), c.xy.data(), 1, neg_c.xy.data()));
+  return pairing_product_is_one({proof, neg_c}, {g2, g2_pow_maxd_minus_d}, pk);
+}
 // commit_kzg (kzg.rs:57-59)
 inline CommitmentKZG commit_kzg(const Polynomial& f, const PublicKeyKZG& pk) {
   G1Point c;

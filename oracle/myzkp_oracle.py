@@ -17,7 +17,9 @@ the reference.  What is pinned (tests/test_oracle_kats.py): every known-answer
 test the reference holds under this path - bn128.rs:285-301 (test_g1),
 bn128.rs:240-251 (test_fq), field.rs:443-550, polynomial.rs:727-768,805-821,
 cuda/test_fr.cu:5-42, gemini.rs:288-307 / book gemini.md:311-328 - plus the
-public EIP-196 value of 2G and the algebraic identity C == [f(alpha)]G.
+public EIP-196 value of 2G and the algebraic identity C == [f(alpha)]G.  The G2 / Fq2 / Fq12 / pairing
+restatements (bn128.rs:33-181, efield.rs, curve.rs:285-339) are pinned by bn128.rs:254-365 (test_fq2, test_g2,
+test_g12, test_pairing) and the public value of 2*G2.
 """
 from __future__ import annotations
 
@@ -435,7 +437,7 @@ class Polynomial:
 
 # --- kzg.rs -----------------------------------------------------------------
 class PublicKeyKZG:
-    """kzg.rs:8-11 (powers_2 / G2 is verifier-side and out of scope)."""
+    """kzg.rs:8-11 (powers_1; the G2 half is restated separately by setup_kzg_g2)."""
 
     def __init__(self, powers_1: List[G1Point]):
         self.powers_1 = powers_1

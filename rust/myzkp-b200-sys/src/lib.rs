@@ -35,6 +35,8 @@ extern "C" {
     pub fn myzkp_srs_generate_g2(ctx: *mut myzkp_ctx, alpha_le: *const u8, base_or_null: *const u8, first: usize, n: usize,
                                  out: *mut u8) -> c_int;
     pub fn myzkp_srs_len(ctx: *const myzkp_ctx) -> usize;
+    pub fn myzkp_pairing(ctx: *mut myzkp_ctx, g1: *const u8, g2: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn myzkp_pairing_product_is_one(ctx: *mut myzkp_ctx, g1: *const u8, g2: *const u8, n: usize, out_is_one: *mut c_int) -> c_int;
     pub fn myzkp_g2_msm(ctx: *mut myzkp_ctx, scalars_le: *const u8, points: *const u8, n: usize, out: *mut u8) -> c_int;
 
     pub fn myzkp_kzg_commit(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, out_c: *mut u8) -> c_int;

@@ -12,6 +12,7 @@ use myzkp::modules::algebra::polynomial::Polynomial;
 use myzkp::modules::algebra::ring::Ring;
 use myzkp_b200_sys as sys;
 use num_bigint::{BigInt, Sign};
+use num_traits::Zero;
 
 pub type CommitmentKZG = G1Point;
 
@@ -140,6 +141,41 @@ pub fn accumulate_curve_points_g2(g_vec: &[G2Point], assignment: &[FqOrder], pk:
     let mut out = [0u8; 128];
     check(pk.ctx, unsafe { sys::myzkp_g2_msm(pk.ctx, scalars.as_ptr(), pts.as_ptr(), n, out.as_mut_ptr()) });
     g2_from_bytes(&out)
+}
+
+fn g1_to_bytes(p: &G1Point) -> [u8; 64] {
+    let mut out = [0u8; 64];
+    if let (Some(x), Some(y)) = (&p.x, &p.y) {
+        out[..32].copy_from_slice(&fq_to_le(x));
+        out[32..].copy_from_slice(&fq_to_le(y));
+    }
+    out
+}
+
+/// prod_i e(g1[i], g2[i]) == 1 on the GPU: the Miller loops run side by side, one final exponentiation
+/// (optimal_ate_pairing, curve/bn128.rs:147-181).
+pub fn pairing_product_is_one(g1: &[G1Point], g2: &[G2Point], pk: &GpuPublicKeyKZG) -> bool {
+    let n = g1.len().min(g2.len());
+    let a: Vec<u8> = g1[..n].iter().flat_map(|p| g1_to_bytes(p)).collect();
+    let b: Vec<u8> = g2[..n].iter().flat_map(|p| g2_to_bytes(p)).collect();
+    let mut ok: std::os::raw::c_int = 0;
+    check(pk.ctx, unsafe { sys::myzkp_pairing_product_is_one(pk.ctx, a.as_ptr(), b.as_ptr(), n, &mut ok) });
+    ok != 0
+}
+
+/// verify_kzg (kzg.rs:90-102): e(C, g2) == e(W, [alpha]g2 - [u]g2) * e(g1, g2)^y, evaluated as the product
+/// e(C, g2) * e(-W, [alpha - u]g2) * e([-y]g1, g2) == 1.  The three small group operations use the reference's
+/// own point arithmetic; the pairings run on the GPU.
+pub fn verify_kzg(u: &FqOrder, c: &CommitmentKZG, proof: &ProofKZG, g1: &G1Point, pk: &GpuPublicKeyKZG) -> bool {
+    let g2 = &pk.powers_2[0];
+    let g2_alpha_minus_u = pk.powers_2[1].clone() - g2.mul_ref(u.clone().get_value());
+    let minus_y = (FqOrder::zero() - proof.y.clone()).sanitize();
+    let g1_minus_y = g1.mul_ref(minus_y.get_value());
+    pairing_product_is_one(
+        &[c.clone(), -proof.w.clone(), g1_minus_y],
+        &[g2.clone(), g2_alpha_minus_u, g2.clone()],
+        pk,
+    )
 }
 
 /// commit_kzg (kzg.rs:57-59)

@@ -54,6 +54,12 @@ int main() {
       auto p2 = powers_2(pk, scalar_u64(2), 2);
       printf("G2.2x0 %s\n", hex_be(p2[1].xy.data()).c_str());
       if (p2.size() != 2 || p2[0].is_point_at_infinity() || p2[1] == p2[0]) { printf("FAIL powers_2\n"); return 1; }
+      // pairing product: e(g, g2) e(-g, g2) == 1, and != 1 against 2 g2 (the shape of verify_degree_bound, kzg.rs:136-144)
+      G1Point g = pk.powers_1()[0];
+      if (!verify_degree_bound(g, g, pk, p2[0], p2[0]) || verify_degree_bound(g, g, pk, p2[0], p2[1])) {
+        printf("FAIL pairing product\n");
+        return 1;
+      }
     }
     // range-sharded commit inside one process: two ranks (own threads), exchange over peer memory
     {

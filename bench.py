@@ -464,6 +464,19 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
         ex[f"commit_2^{lg}_ms"] = ms_c
         ex[f"open_2^{lg}_ms"] = ms_o
         ex[f"commit_2^{lg}_points_per_s"] = n / (ms_c * 1e-3)
+    # secondary scalar distributions of SURVEY 8d at 2^20 (reported, not headline): (B) byte-valued scalars as the DAS
+    # callers produce (avail.rs:93), (Z) 10 % zeros
+    if log2n >= 20:
+        n = 1 << 20
+        rng = np.random.Generator(np.random.PCG64(synth.SEED_SCALARS + 77))
+        byte_sc = np.zeros((n, 4), dtype=np.uint64)
+        byte_sc[:, 0] = rng.integers(0, 256, size=n, dtype=np.uint64)
+        zero_sc = synth.random_scalars(n, synth.SEED_SCALARS + 78)
+        zero_sc[rng.random(n) < 0.10] = 0
+        for name, arr in (("bytes", byte_sc), ("10pct_zeros", zero_sc)):
+            sc = torch.from_numpy(arr.view(np.int64).reshape(-1)).to(dev)
+            ex[f"commit_2^20_{name}_ms"] = timeit(lambda: ctx.commit_dev(sc.data_ptr(), n, out.data_ptr()))
+        del sc
     # HBM-bound scalar-field phases of open (64 B per coefficient algorithmic)
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -5,9 +5,10 @@
 //
 // Pipeline (all on the ctx stream, no host round trips):
 //   1. msm_recode      scalar -> W signed c-bit digits; one (bucket key, table
-//                      index | sign) entry per non-zero digit.  Because table
-//                      row j holds 2^(8j) P_i, every window shares ONE set of
-//                      2^(c-1) buckets and no doublings are ever needed.
+//                      index | sign) entry per non-zero digit.  Because the table
+//                      holds 2^(c w) P_i for every window w (rows at the bit offsets
+//                      of ctx->row_bits), every window shares ONE set of 2^(c-1)
+//                      buckets and no doublings are ever needed.
 //   2. radix sort      entries by bucket key (sort.cu: hand-written LSD radix sort,
 //                      8 bits per pass, c bits).
 //   3. msm_accumulate  fixed-length segments of the sorted entry list, one

@@ -197,6 +197,87 @@ pub fn open_kzg(f: &Polynomial<FqOrder>, u: &FqOrder, pk: &GpuPublicKeyKZG) -> P
     ProofKZG { y: FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, &y)), w: point_from_bytes(&w) }
 }
 
+pub struct BatchProofKZG {
+    pub ys: Vec<FqOrder>,
+    pub w: G1Point,
+}
+pub type ProofDegreeBound = G1Point;
+
+/// batch_open_kzg (kzg.rs:74-88): ys[i] = f(us[i]) and W = commit((f - I) / prod (x - us[i])) on the GPU
+pub fn batch_open_kzg(f: &Polynomial<FqOrder>, us: &[FqOrder], pk: &GpuPublicKeyKZG) -> BatchProofKZG {
+    let bytes = marshal_scalars(&f.coef);
+    let ub = marshal_scalars(us);
+    let mut ys = vec![0u8; 32 * us.len()];
+    let mut w = [0u8; 64];
+    check(pk.ctx, unsafe {
+        sys::myzkp_kzg_batch_open(pk.ctx, bytes.as_ptr(), f.coef.len(), ub.as_ptr(), us.len(), ys.as_mut_ptr(), w.as_mut_ptr())
+    });
+    BatchProofKZG {
+        ys: ys.chunks_exact(32).map(|c| FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, c))).collect(),
+        w: point_from_bytes(&w),
+    }
+}
+
+/// prove_degree_bound (kzg.rs:121-134): an MSM of f against the SRS window starting at max_d - d
+pub fn prove_degree_bound(f: &Polynomial<FqOrder>, pk: &GpuPublicKeyKZG, d: usize) -> ProofDegreeBound {
+    let bytes = marshal_scalars(&f.coef);
+    let mut out = [0u8; 64];
+    check(pk.ctx, unsafe { sys::myzkp_kzg_prove_degree_bound(pk.ctx, bytes.as_ptr(), f.coef.len(), d, out.as_mut_ptr()) });
+    point_from_bytes(&out)
+}
+
+/// verify_degree_bound (kzg.rs:136-144) as e(proof, g2) * e(-c, [alpha^(max_d - d)]g2) == 1; needs the full G2 powers
+pub fn verify_degree_bound(c: &CommitmentKZG, proof: &ProofDegreeBound, pk: &GpuPublicKeyKZG, d: usize) -> bool {
+    let max_d = unsafe { sys::myzkp_srs_len(pk.ctx) } - 1;
+    pairing_product_is_one(&[proof.clone(), -c.clone()], &[pk.powers_2[0].clone(), pk.powers_2[max_d - d].clone()], pk)
+}
+
+pub struct ProofGemini {
+    pub es: Vec<BatchProofKZG>,
+    pub degree_proofs: Vec<ProofDegreeBound>,
+}
+
+/// split_and_fold (gemini.rs:51-103) fused with commit_gemini (gemini.rs:112-114): the folds are computed and committed
+/// on the GPU; returns the log2(n) + 1 commitments and the folded polynomials (without the original).
+pub fn split_and_fold_commit(coef: &[FqOrder], rhos: &[FqOrder], pk: &GpuPublicKeyKZG) -> (Vec<CommitmentKZG>, Vec<Polynomial<FqOrder>>) {
+    let n = coef.len();
+    let m = rhos.len();
+    let (cb, rb) = (marshal_scalars(coef), marshal_scalars(rhos));
+    let mut out = vec![0u8; 64 * (m + 1)];
+    let mut folds = vec![0u8; 32 * n.saturating_sub(1)];
+    // non power-of-two n / wrong challenge count come back as an error (SplitFoldError, gemini.rs:55-66)
+    check(pk.ctx, unsafe {
+        sys::myzkp_gemini_fold_commit(pk.ctx, cb.as_ptr(), n, rb.as_ptr(), out.as_mut_ptr(), folds.as_mut_ptr())
+    });
+    let cms = out.chunks_exact(64).map(|c| point_from_bytes(c.try_into().unwrap())).collect();
+    let mut polys = Vec::with_capacity(m);
+    let (mut off, mut len) = (0usize, n / 2);
+    while len >= 1 {
+        let coef = folds[32 * off..32 * (off + len)]
+            .chunks_exact(32)
+            .map(|c| FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, c)))
+            .collect();
+        polys.push(Polynomial { coef });
+        off += len;
+        len /= 2;
+    }
+    (cms, polys)
+}
+
+/// open_gemini (gemini.rs:116-144)
+pub fn open_gemini(polys: &[Polynomial<FqOrder>], beta: &FqOrder, pk: &GpuPublicKeyKZG) -> ProofGemini {
+    let num_polys = polys.len();
+    let us = vec![beta.clone(), (FqOrder::zero() - beta.clone()).sanitize(), beta.pow(2)];
+    ProofGemini {
+        es: polys.iter().take(num_polys - 1).map(|p| batch_open_kzg(p, &us, pk)).collect(),
+        degree_proofs: polys
+            .iter()
+            .enumerate()
+            .map(|(i, p)| prove_degree_bound(p, pk, 2_usize.pow((num_polys - i - 1) as u32)))
+            .collect(),
+    }
+}
+
 /// commit_gemini (gemini.rs:112-114): one batched call (small polynomials run concurrently on the GPU)
 pub fn commit_gemini(polys: &[Polynomial<FqOrder>], pk: &GpuPublicKeyKZG) -> Vec<CommitmentKZG> {
     let bufs: Vec<Vec<u8>> = polys.iter().map(|p| marshal_scalars(&p.coef)).collect();

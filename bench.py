@@ -130,7 +130,8 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "g1_msm_points_per_sec", "value": val, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
-        "config": {"workload": f"kzg_commit_deg2^{log2n} (G1 MSM, 2^{log2n} BN128 points)", "sample_points": sample},
+        "config": {"workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
+                   "sample_points": sample},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": desc,
                          "value_1core": v1},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

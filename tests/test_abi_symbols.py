@@ -44,3 +44,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "myzkp_oracle" not in text and "oracle/" not in text.replace("the oracle", ""), f
+
+
+def test_header_is_plain_c_and_mirrors_agree():
+    """The boundary is a C ABI: the header must compile as C99, and the Rust `-sys` crate (shipped as source) must
+    declare exactly the header's entry points."""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write('#include "myzkp_b200.h"\nint main(void) { return 0; }\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                               "-I", os.path.join(ROOT, "include"), src])
+    rs = open(os.path.join(ROOT, "rust", "myzkp-b200-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (myzkp_[a-z0-9_]+)\s*\(", rs)))
+    missing = [n for n in _declared() if n not in rust]
+    extra = [n for n in rust if n not in _declared()]
+    assert not missing and not extra, (missing, extra)

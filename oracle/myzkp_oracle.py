@@ -13,7 +13,8 @@ relative to /root/reference/myzkp/src/modules/algebra/.
 Parity pinning: the reference cannot be compiled here (Rust toolchain absent)
 and its own KZG tests are pairing-verified property tests with an unseeded
 random alpha (kzg.rs:152-175), so commitment coordinates are *not* pinned by
-the reference.  What is pinned (tests/test_oracle_kats.py): every known-answer
+the reference; what those tests check - verify_kzg accepts - is restated here too (optimal_ate_pairing,
+verify_kzg) and holds for this oracle's own commitments and proofs.  What is pinned (tests/test_oracle_kats.py): every known-answer
 test the reference holds under this path - bn128.rs:285-301 (test_g1),
 bn128.rs:240-251 (test_fq), field.rs:443-550, polynomial.rs:727-768,805-821,
 cuda/test_fr.cu:5-42, gemini.rs:288-307 / book gemini.md:311-328 - plus the

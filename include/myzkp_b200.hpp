@@ -89,15 +89,68 @@ inline bool pairing_product_is_one(const std::vector<G1Point>& g1, const std::ve
   pk.check(myzkp_pairing_product_is_one(pk.ctx(), n ? g1[0].xy.data() : nullptr, n ? g2[0].xy.data() : nullptr, n, &ok));
   return ok != 0;
 }
-// verify_degree_bound (kzg.rs:136-144): e(proof, g2) == e(c, [alpha^(max_d - d)]g2), with c negated by the caller's
-// field arithmetic replaced by a G1 MSM with scalar r - 1
+// r - x for a canonical scalar x (0 stays 0): the shim's FqOrder negation, done on the wire bytes
+inline Scalar scalar_neg(const Scalar& x) {
+  static const Scalar r = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                           0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+  bool zero = true;
+  for (uint8_t b : x) zero = zero && b == 0;
+  Scalar out{};
+  if (zero) return out;
+  int borrow = 0;
+  for (int i = 0; i < 32; i++) {
+    int d = (int)r[i] - (int)x[i] - borrow;
+    borrow = d < 0;
+    out[i] = (uint8_t)(d + (borrow << 8));
+  }
+  return out;
+}
+inline Scalar scalar_one() {
+  Scalar s{};
+  s[0] = 1;
+  return s;
+}
+// -P through the device group law (a G1 MSM with the scalar r - 1)
+inline G1Point g1_neg(const G1Point& p, const PublicKeyKZG& pk) {
+  G1Point out;
+  const Scalar m1 = scalar_neg(scalar_one());
+  pk.check(myzkp_g1_msm(pk.ctx(), m1.data(), p.xy.data(), 1, out.xy.data()));
+  return out;
+}
+// verify_degree_bound (kzg.rs:136-144): e(proof, g2) == e(c, [alpha^(max_d - d)]g2) as a product with -c
 inline bool verify_degree_bound(const CommitmentKZG& c, const G1Point& proof, const PublicKeyKZG& pk, const G2Point& g2,
                                 const G2Point& g2_pow_maxd_minus_d) {
-  Scalar minus_one = {0x00, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
-                      0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};  // r - 1
-  G1Point neg_c;
-  pk.check(myzkp_g1_msm(pk.ctx(), minus_one.data(), c.xy.data(), 1, neg_c.xy.data()));
-  return pairing_product_is_one({proof, neg_c}, {g2, g2_pow_maxd_minus_d}, pk);
+  return pairing_product_is_one({proof, g1_neg(c, pk)}, {g2, g2_pow_maxd_minus_d}, pk);
+}
+// verify_kzg (kzg.rs:90-102): e(C, g2) == e(W, [alpha]g2 - [u]g2) * e(g1, g2)^y, evaluated as
+// e(C, g2) * e(-W, [alpha - u]g2) * e([-y]g1, g2) == 1; p2 = [g2, [alpha]g2] (kzg.rs:37)
+inline bool verify_kzg(const Scalar& u, const CommitmentKZG& c, const ProofKZG& proof, const PublicKeyKZG& pk,
+                       const std::vector<G2Point>& p2) {
+  const std::vector<G1Point> g1 = {pk.powers_1().at(0)};
+  const G2Point g2_alpha_minus_u = accumulate_curve_points({p2.at(1), p2.at(0)}, {scalar_one(), scalar_neg(u)}, pk);
+  G1Point g1_minus_y;
+  const Scalar my = scalar_neg(proof.y);
+  pk.check(myzkp_g1_msm(pk.ctx(), my.data(), g1[0].xy.data(), 1, g1_minus_y.xy.data()));
+  return pairing_product_is_one({c, g1_neg(proof.w, pk), g1_minus_y}, {p2.at(0), g2_alpha_minus_u, p2.at(0)}, pk);
+}
+// batch_open_kzg (kzg.rs:74-88)
+struct BatchProofKZG {
+  std::vector<Scalar> ys;
+  G1Point w;
+};
+inline BatchProofKZG batch_open_kzg(const Polynomial& f, const std::vector<Scalar>& us, const PublicKeyKZG& pk) {
+  BatchProofKZG p;
+  p.ys.resize(us.size());
+  pk.check(myzkp_kzg_batch_open(pk.ctx(), f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(),
+                                us.empty() ? nullptr : us[0].data(), us.size(), us.empty() ? nullptr : p.ys[0].data(),
+                                p.w.xy.data()));
+  return p;
+}
+// prove_degree_bound (kzg.rs:121-134)
+inline G1Point prove_degree_bound(const Polynomial& f, const PublicKeyKZG& pk, size_t d) {
+  G1Point out;
+  pk.check(myzkp_kzg_prove_degree_bound(pk.ctx(), f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(), d, out.xy.data()));
+  return out;
 }
 // commit_kzg (kzg.rs:57-59)
 inline CommitmentKZG commit_kzg(const Polynomial& f, const PublicKeyKZG& pk) {

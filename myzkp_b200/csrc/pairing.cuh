@@ -252,4 +252,148 @@ MZ_HD void pairing_final_exp(Exec& ex, F12& f, F12& base, F12& acc) {
   ex.sync();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Final exponentiation by parts - the same power (p^12-1)/r = (p^6-1)(p^2+1) * (p^4-p^2+1)/r, about 330
+// Fq12 products instead of 4 200:
+//   easy part  f^(p^6-1) = conj6(f) / f  (conj6 = w -> -w = Frobenius^6), then ^(p^2+1) by one Frobenius;
+//   hard part  (p^4-p^2+1)/r = l0 + l1 p + l2 p^2 + p^3 with, for the BN parameter x = 4965661367192848881,
+//              l2 = 6x^2+1, l1 = -36x^3-18x^2-12x+1, l0 = -36x^3-30x^2-18x-2  (checked numerically);
+//              after the easy part f is unitary, so negative powers are conj6.
+// Validated on the host emulation against the plain power (tests/test_emul_cpu.py); the kernels switch to it
+// with MZ_PAIRING_FAST_FINAL_EXP (off until it has run on the GPU once).
+namespace pairing_const {
+// g_j = xi^((p^j - 1)/6), j = 1, 2, 3, raw limbs c0 | c1: the Frobenius p^j maps w^k to w^k g_j^k
+MZ_HD constexpr uint32_t frob12(int j, int i) {
+  constexpr uint32_t t[3][16] = {
+      {0xdcc9e470u, 0xd60b35dau, 0x292f2176u, 0x5c521e08u, 0x76e68b60u, 0xe8b99fddu, 0x2865a7dfu, 0x1284b71cu,
+       0x80f362acu, 0xca5cf05fu, 0x8eeec7e5u, 0x74799277u, 0x12150b8eu, 0xa6327cfeu, 0xb4fae7e6u, 0x246996f3u},
+      {0x607cfd49u, 0xe4bd44e5u, 0xbb966e3du, 0xc28f069fu, 0xe0acccb0u, 0x5e6dd9e7u, 0xe131a029u, 0x30644e72u,
+       0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+      {0x1ed4a67fu, 0xe86f7d39u, 0xbe55d24au, 0x894cb38du, 0xd0acaa90u, 0xefe9608cu, 0xcc82e4bbu, 0x19dc81cfu,
+       0xf4c0c101u, 0x7694aa2bu, 0x97d439ecu, 0x7f03a5e3u, 0x3576139du, 0x06cbeee3u, 0x0be77d73u, 0x00abf8b6u},
+  };
+  return t[j][i];
+}
+MZ_HD Fq2 frob12_const(int j) {
+  Fq2 r;
+  Fq a, b;
+  for (int i = 0; i < 8; i++) { a.v[i] = frob12(j, i); b.v[i] = frob12(j, 8 + i); }
+  r.c0 = fe_to_mont(a);
+  r.c1 = fe_to_mont(b);
+  return r;
+}
+constexpr uint64_t kBnX = 4965661367192848881ull;
+}  // namespace pairing_const
+
+// leader-only helpers (out must not alias a)
+MZ_HD void f12_conj6(F12& out, const F12& a) {
+#pragma unroll 1
+  for (int k = 0; k < 12; k++) out.c[k] = (k & 1) ? fe_neg(a.c[k]) : a.c[k];
+}
+// out = a^(p^j), j = 1..3: sum_k c_k w^k g^k with g^k = (A + 9B... ) written as (a - 9b) + b w^6
+MZ_HD void f12_frobenius(F12& out, const F12& a, int j) {
+  const Fq2 g = pairing_const::frob12_const(j - 1);
+  Fq2 gam = f2_one();
+#pragma unroll 1
+  for (int k = 0; k < 12; k++) out.c[k] = Fq::zero();
+#pragma unroll 1
+  for (int k = 0; k < 12; k++) {
+    const Fq A = fe_sub(gam.c0, fe_mul_small(gam.c1, 9));
+    const Fq cb = fe_mul(a.c[k], gam.c1);
+    out.c[k] = fe_add(out.c[k], fe_mul(a.c[k], A));
+    if (k + 6 < 12) {
+      out.c[k + 6] = fe_add(out.c[k + 6], cb);
+    } else {  // w^(k+6) = w^(k-6) (18 w^6 - 82)
+      out.c[k] = fe_add(out.c[k], fe_mul_small(cb, 18));
+      out.c[k - 6] = fe_sub(out.c[k - 6], fe_mul_small(cb, 82));
+    }
+    gam = f2_mul(gam, g);
+  }
+}
+// out = n^-1 for n in Fq6 = Fq2[v]/(v^3 - xi), v = w^2, given and returned as an F12 with even coefficients only
+MZ_HD void f12_inv_fq6(F12& out, const F12& n) {
+  Fq2 xi;
+  xi.c0 = fe_mul_small(Fq::one(), 9);
+  xi.c1 = Fq::one();
+  Fq2 m[3];
+  for (int j = 0; j < 3; j++) {
+    m[j].c0 = fe_add(n.c[2 * j], fe_mul_small(n.c[2 * j + 6], 9));
+    m[j].c1 = n.c[2 * j + 6];
+  }
+  Fq2 t0 = f2_sub(f2_sqr(m[0]), f2_mul(xi, f2_mul(m[1], m[2])));
+  Fq2 t1 = f2_sub(f2_mul(xi, f2_sqr(m[2])), f2_mul(m[0], m[1]));
+  Fq2 t2 = f2_sub(f2_sqr(m[1]), f2_mul(m[0], m[2]));
+  Fq2 d = f2_add(f2_mul(m[0], t0), f2_mul(xi, f2_add(f2_mul(m[2], t1), f2_mul(m[1], t2))));
+  Fq2 di = f2_inv(d);
+  Fq2 r[3] = {f2_mul(t0, di), f2_mul(t1, di), f2_mul(t2, di)};
+#pragma unroll 1
+  for (int k = 0; k < 12; k++) out.c[k] = Fq::zero();
+  for (int j = 0; j < 3; j++) {
+    out.c[2 * j] = fe_sub(r[j].c0, fe_mul_small(r[j].c1, 9));
+    out.c[2 * j + 6] = r[j].c1;
+  }
+}
+
+// out = a^e for a small public exponent e >= 1 (out must not alias a)
+template <class Exec>
+MZ_HD void f12_pow_u64(Exec& ex, F12& out, const F12& a, uint64_t e) {
+  int top = 63;
+  while (top > 0 && !((e >> top) & 1ull)) top--;
+  if (ex.leader()) out = a;
+  ex.sync();
+  for (int bit = top - 1; bit >= 0; bit--) {
+    ex.mul(out, out, out);
+    if ((e >> bit) & 1ull) ex.mul(out, out, a);
+  }
+}
+
+// f <- f^((p^12-1)/r); w: nine F12 of working storage every lane of the executor can reach
+template <class Exec>
+MZ_HD void pairing_final_exp_fast(Exec& ex, F12& f, F12* w) {
+  // easy part
+  if (ex.leader()) f12_conj6(w[0], f);
+  ex.sync();
+  ex.mul(w[1], f, w[0]);  // norm to Fq6 (odd coefficients vanish)
+  if (ex.leader()) f12_inv_fq6(w[2], w[1]);
+  ex.sync();
+  ex.mul(w[1], w[0], w[2]);  // 1 / f
+  ex.mul(w[1], w[0], w[1]);  // f^(p^6 - 1)
+  if (ex.leader()) f12_frobenius(w[0], w[1], 2);
+  ex.sync();
+  ex.mul(w[1], w[0], w[1]);  // ^(p^2 + 1): unitary from here on; w[1] = g
+  // hard part
+  f12_pow_u64(ex, w[2], w[1], pairing_const::kBnX);  // g^x
+  f12_pow_u64(ex, w[3], w[2], pairing_const::kBnX);  // g^(x^2)
+  f12_pow_u64(ex, w[4], w[3], pairing_const::kBnX);  // g^(x^3)
+  f12_pow_u64(ex, w[5], w[3], 6);
+  ex.mul(w[5], w[5], w[1]);                          // y2 = g^(6x^2 + 1)
+  f12_pow_u64(ex, w[7], w[4], 36);                   // g^(36 x^3)
+  f12_pow_u64(ex, w[0], w[3], 18);
+  ex.mul(w[6], w[7], w[0]);
+  f12_pow_u64(ex, w[0], w[2], 12);
+  ex.mul(w[6], w[6], w[0]);                          // g^(36x^3 + 18x^2 + 12x)
+  if (ex.leader()) f12_conj6(w[0], w[6]);
+  ex.sync();
+  ex.mul(w[6], w[0], w[1]);                          // y1 = g^(-36x^3 - 18x^2 - 12x + 1)
+  f12_pow_u64(ex, w[0], w[3], 30);
+  ex.mul(w[7], w[7], w[0]);
+  f12_pow_u64(ex, w[0], w[2], 18);
+  ex.mul(w[7], w[7], w[0]);
+  ex.mul(w[7], w[7], w[1]);
+  ex.mul(w[7], w[7], w[1]);                          // g^(36x^3 + 30x^2 + 18x + 2)
+  if (ex.leader()) f12_conj6(w[8], w[7]);            // y0
+  ex.sync();
+  if (ex.leader()) f12_frobenius(w[0], w[6], 1);
+  ex.sync();
+  ex.mul(w[8], w[8], w[0]);                          // y0 * y1^p
+  if (ex.leader()) f12_frobenius(w[0], w[5], 2);
+  ex.sync();
+  ex.mul(w[8], w[8], w[0]);                          // * y2^(p^2)
+  if (ex.leader()) f12_frobenius(w[0], w[1], 3);
+  ex.sync();
+  ex.mul(w[8], w[8], w[0]);                          // * g^(p^3)
+  if (ex.leader()) f = w[8];
+  ex.sync();
+}
+
 }  // namespace mz

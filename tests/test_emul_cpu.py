@@ -250,6 +250,14 @@ def test_pairing_emulated():
         L.emul_f12_mul(enc12(x), enc12(y), out)
         assert dec12(out) == (o.Fq12(x) * o.Fq12(y)).c
 
+    # final exponentiation by parts == the plain power, on arbitrary (non-unitary) elements and on a Miller value
+    for _ in range(3):
+        x = [rnd.randrange(P) for _ in range(12)]
+        slow, fast = A96(), A96()
+        L.emul_final_exp(enc12(x), 0, slow)
+        L.emul_final_exp(enc12(x), 1, fast)
+        assert dec12(fast) == dec12(slow) == o.Fq12(x).pow(o.FINAL_EXPONENT).c
+
     def enc1(pt):
         vals = [0, 0] if pt is None else list(pt)
         return (ctypes.c_uint32 * 16)(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vals for i in range(8)])
@@ -267,6 +275,9 @@ def test_pairing_emulated():
         return o.optimal_ate_pairing(o.generator_g1().mul_ref(k1), o.generator_g2().mul_ref(k2)).c
 
     one = [1] + [0] * 11
+    out = A96()
+    L.emul_pairing(enc1(o.fast_mul(5)), enc2(o.g2_fast_mul(11)), 2, out)  # Miller loop + final exponentiation by parts
+    assert dec12(out) == oracle_pairing(55, 1)
     assert pairing(o.fast_mul(1), o.g2_fast_mul(1)) == oracle_pairing(1, 1)
     assert pairing(o.fast_mul(37), o.g2_fast_mul(27)) == oracle_pairing(999, 1)  # bn128.rs:362-364
     assert pairing(None, o.g2_fast_mul(3)) == one and pairing(o.fast_mul(3), None) == one

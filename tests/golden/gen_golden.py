@@ -71,7 +71,13 @@ def main():
                                  ("alpha_zero", 0, 3, g2)]:
         g2s.append({"name": name, "alpha": str(alpha), "base": pt2(base), "powers_2": [pt2(p) for p in o.setup_kzg_g2(base, alpha, n)]})
         print(name, "done", file=sys.stderr)
-    out = {"generator": "tests/golden/gen_golden.py (faithful oracle path)", "kzg": cases, "gemini": gem, "g2": g2s}
+    # pairing values (optimal_ate_pairing, bn128.rs:147-181) as the 12 coefficients of w^k
+    pair = []
+    for k1, k2 in [(1, 1), (37, 27)]:
+        e = o.optimal_ate_pairing(o.generator_g1().mul_ref(k1), g2.mul_ref(k2))
+        pair.append({"g1_multiple": k1, "g2_multiple": k2, "fq12": [str(v) for v in e.c]})
+        print("pairing", k1, k2, "done", file=sys.stderr)
+    out = {"generator": "tests/golden/gen_golden.py (faithful oracle path)", "kzg": cases, "gemini": gem, "g2": g2s, "pairing": pair}
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_golden.json"), "w") as fh:
         json.dump(out, fh, indent=1)
 

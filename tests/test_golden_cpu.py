@@ -40,3 +40,15 @@ def test_golden_g2_matches_fast_path():
         alpha, base = int(case["alpha"]), _pt2(case["base"])
         for i, p in enumerate(case["powers_2"]):
             assert o.g2_fast_mul(pow(alpha, i, o.R_MOD), base) == _pt2(p), case["name"]
+
+
+def test_golden_pairing_values():
+    """The committed pairing values are what the oracle's restatement of optimal_ate_pairing gives, and they are bilinear:
+    e(37 G1, 27 G2) = e(G1, G2)^999 (bn128.rs:362-364)."""
+    vals = {}
+    for case in G["pairing"]:
+        k1, k2 = int(case["g1_multiple"]), int(case["g2_multiple"])
+        e = o.optimal_ate_pairing(o.generator_g1().mul_ref(k1), o.generator_g2().mul_ref(k2))
+        assert e.c == [int(v) for v in case["fq12"]], (k1, k2)
+        vals[(k1, k2)] = e
+    assert vals[(1, 1)].pow(999) == vals[(37, 27)]

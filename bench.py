@@ -99,41 +99,43 @@ class ClockSampler(threading.Thread):
 # reference arm: the oracle port (C restatement of the reference's naive algorithm) on the host
 # --------------------------------------------------------------------------------------
 def run_reference(args, rank: int, world: int):
+    """The reference's own algorithm (C port, oracle/oracle.c) on ONE host core - the reference is single-threaded, so
+    this is what it would do on this box and the figure does not depend on the host's core count.  The same sample
+    on all host threads is reported beside it as a labelled extra."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c as oc
     from myzkp_b200 import synth
 
-    threads = os.cpu_count() or 1
-    sample = args.cpu_sample
+    all_threads = os.cpu_count() or 1
+    sample = args.ref_sample
     log2n = args.log2n
     alpha = synth.random_scalar(synth.SEED_ALPHA)
-    srs = oc.setup_kzg_bytes(alpha, sample, threads=threads)  # untimed fixture (kzg.rs:27-40)
+    srs = oc.setup_kzg_bytes(alpha, sample, threads=all_threads)  # untimed fixture (kzg.rs:27-40)
     coefs = synth.random_scalars(sample, synth.SEED_SCALARS + log2n).tobytes()
-    for _ in range(args.warmup):
-        oc.commit_kzg_bytes(coefs, srs, sample, threads)
+    for _ in range(min(args.warmup, 2)):
+        oc.commit_kzg_bytes(coefs, srs, sample, 1)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oc.commit_kzg_bytes(coefs, srs, sample, threads)
+        oc.commit_kzg_bytes(coefs, srs, sample, 1)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     t1 = time.perf_counter()
-    one = min(sample, 256)
-    oc.commit_kzg_bytes(coefs, srs, one, 1)
-    v1 = one / (time.perf_counter() - t1)
+    oc.commit_kzg_bytes(coefs, srs, sample, all_threads)
+    v_all = sample / (time.perf_counter() - t1)
     desc = (f"naive commit_kzg (affine double-and-add, ext-Euclid inversion per add; polynomial.rs:156-165) of the first "
-            f"{sample} coefficients of the 2^{log2n} workload per step, {threads} host threads splitting the index range "
-            f"(the reference itself is single-threaded: {v1:.0f} points/s on 1 core); reference is Rust and cannot be "
-            f"built in this image, so this is the C port oracle/oracle.c")
+            f"{sample} coefficients of the 2^{log2n} workload per step on 1 host core (the reference is single-threaded); "
+            f"the reference is Rust and cannot be built in this image, so this is the C port oracle/oracle.c")
     line = {
         "impl": "reference", "metric": "g1_msm_points_per_sec", "value": val, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
                    "sample_points": sample},
-        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": desc,
-                         "value_1core": v1},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": 1, "kind": "port", "sample": desc},
+        "all_host_threads": {"value": v_all, "unit": "points/s", "cores": all_threads,
+                             "note": "same sample with the index range split over every host thread (not how the reference runs)"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -166,11 +168,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--log2n", type=int, default=24)
     ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--ref-sample", type=int, default=512, help="--impl reference: coefficients per step (1 core, ~3.4 ms each)")
     ap.add_argument("--no-verify", action="store_true", help="skip the O(N) host check of the full-size commitment")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory exchange kernel (default) or NCCL all_gather + sum")
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--table-windows", default="", help="comma list of MSM windows the SRS table should support (default: all, 70 rows)")
     ap.add_argument("--segment-len", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -214,8 +218,11 @@ def main():
     # ---- fixtures: SRS shard (resident) and scalars --------------------------------
     alpha = synth.random_scalar(synth.SEED_ALPHA)
     t0 = time.perf_counter()
+    if args.table_windows:
+        ctx.set_table_windows([int(c) for c in args.table_windows.split(",")])
     ctx.srs_generate(alpha, n_local, first=lo)
     t_srs = time.perf_counter() - t0
+    tinfo = ctx.table_info()
     scal_all = synth.random_scalars(n_total, synth.SEED_SCALARS + log2n)  # same on every rank
     pinned = ctx.host_alloc(max(n_local, 1) * 32)
     pinned[: n_local * 32] = scal_all[lo:hi].view(np.uint8).reshape(-1)
@@ -253,8 +260,9 @@ def main():
     if rank == 0 and not args.no_verify:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import myzkp_oracle as orc  # the checker only
+        import oracle_c as oc  # the checker only
 
-        fa = synth.horner_mod_r(scal_all, alpha)
+        fa = oc.fr_eval_bytes(scal_all.tobytes(), n_total, alpha)  # f(alpha) on the host
         verified = got == orc.fast_mul(fa)
         if not verified:
             raise SystemExit(f"bench.py: commitment mismatch vs oracle expected value at 2^{log2n}")
@@ -357,14 +365,20 @@ def main():
     if acc_ms > 0:
         achieved = n_local * ALG_IMAD_PER_POINT / (acc_ms * 1e-3) / 1e12
         executed = info.get("entries", 0) * IMAD_PER_MADD / (acc_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic_r1.json"))).get(f"2^{log2n}_n{world}")
-        except Exception:
-            pass
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # kernel at this size (profiles/accumulate_traffic_r2.json); null when no capture exists for this size / N
+        traffic, traffic_src = None, None
+        for name in ("accumulate_traffic_r2.json", "accumulate_traffic_r1.json"):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", name))).get(f"2^{log2n}_n{world}")
+            except Exception:
+                traffic = None
+            if traffic:
+                traffic_src = "profiles/" + name + " (ncu --set full capture, not measured in this run)"
+                break
         roofline = {
             "kernel": "msm_accumulate", "bound": "int32_imad", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD/s",
-            "frac": (achieved / imad_peak) if imad_peak else None, "traffic": traffic,
+            "frac": (achieved / imad_peak) if imad_peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "measured (bench/imad_peak.cu on this pool's B200, profiles/imad_peak_r1.json)" if imad_peak else None,
             "executed_TIMAD_s": executed, "executed_frac": (executed / imad_peak) if imad_peak else None,
             "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step,
@@ -375,6 +389,9 @@ def main():
             gbs = n_local * SORT_BYTES_PER_POINT / (sort_ms * 1e-3) / 1e9
             roofline_hbm = {"kernels": "msm_recode + radix sort", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "phase_ms": sort_ms}
+
+    # ---- the other BASELINE configs at this N: open at 2^24, C3 (2^20 commit + open), C5 (Gemini) ---------------
+    configs = run_configs(args, mz, synth, torch, dist, ctx, ops, prover, d_scal, scal_all, alpha, rank, world, dev, barrier)
 
     # ---- cpu baseline + extras (rank 0, N = 1) -----------------------------------------------
     cpu_baseline = None
@@ -411,8 +428,12 @@ def main():
             "config": {
                 "workload": f"kzg_commit_deg2^{log2n} (one G1 MSM of 2^{log2n} BN128 points per step)",
                 "points_total": n_total, "points_per_gpu": n_local, "parallelism": f"range-sharded x{world}", "exchange": exchange,
-                "l2": "inputs larger than L2 (scalars %d MiB + resident SRS table of 2^(b_j) multiples, >= %d MiB per GPU; no flush needed)"
-                      % (n_local * 32 >> 20, n_local * 64 * 32 >> 20),
+                "l2": "inputs larger than L2 (scalars %d MiB + the rows of the resident SRS table the window uses, %d MiB per GPU; no flush needed)"
+                      % (n_local * 32 >> 20, n_local * 64 * info.get("windows", 12) >> 20),
+                "srs_table": {"rows": tinfo["rows"], "GiB_per_gpu": round(tinfo["bytes"] / 2**30, 2), "windows": tinfo["windows"],
+                              "note": "resident table of 2^(b_j) multiples of every SRS point (the design's price for an MSM "
+                                      "without doublings): rows x 64 B per point; myzkp_ctx_set_table_windows restricts it "
+                                      "(window 22 alone = 12 rows)"},
                 "window_bits": info.get("window_bits"), "srs_setup_s": t_srs,
             },
             "commits_per_sec": 1e3 / ms_step,
@@ -428,11 +449,175 @@ def main():
             "exchange_ms": (ms_step - max(per_rank_local_ms)) if per_rank_local_ms else None,
             "cpu_baseline": cpu_baseline,
             "verified_vs_oracle": verified,
+            "configs": configs,
             "extra": extra,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_configs(args, mz, synth, torch, dist, ctx, ops, prover, d_scal, scal_all, alpha, rank, world, dev, barrier):
+    """BASELINE.json's other configurations on the same N GPUs, each VERIFIED against the oracle's expected values
+    before it is timed (device events on the ctx stream, barrier on both sides, max over ranks):
+      open_2^24   open_kzg of the bench polynomial (north star: commit + open at degree 2^24), range-sharded
+      C3          commit_kzg + open_kzg of a 2^20 polynomial, range-sharded over the N GPUs
+      C5          split_and_fold + the 21 commitments of a 2^20 multilinear (one GPU: only the MSM is sharded, and
+                  Gemini's levels are small - at N > 1 rank 0 runs it alone)"""
+    from myzkp_b200.dist import DeviceOps, ShardedKZG, shard_range
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import myzkp_oracle as orc  # the checker only
+    import oracle_c as oc  # the checker only
+
+    R = mz.R_MOD
+    log2n = args.log2n
+    n_total = 1 << log2n
+    u = synth.random_scalar(synth.SEED_OPEN)
+    steps = max(3, min(args.steps, 10))
+    res = {}
+
+    def timed(fn, reps=steps, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1 and ops.fused:
+            ops.exchange_sum(ops.partial, align_out)  # device-side rendezvous (see align() in main)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / reps
+
+    align_out = torch.zeros(64, dtype=torch.uint8, device=dev)
+    yw = torch.zeros(96, dtype=torch.uint8, device=dev)
+
+    def read_open():
+        raw = yw.cpu().numpy().tobytes()
+        return int.from_bytes(raw[:32], "little"), mz.context.point_from_bytes(raw[32:])
+
+    def expected(coefs_limbs, n):
+        cb = coefs_limbs.tobytes()
+        fa = oc.fr_eval_bytes(cb, n, alpha)
+        y = oc.fr_eval_bytes(cb, n, u)
+        return orc.fast_mul(fa), y, orc.fast_mul((fa - y) * pow((alpha - u) % R, -1, R) % R)
+
+    # ---- open at the bench size ----
+    prover.open(d_scal.data_ptr(), u, yw[:32], yw[32:])
+    torch.cuda.synchronize()
+    got = read_open()
+    ok = None
+    if not args.no_verify:
+        _, y, w = expected(scal_all, n_total)
+        ok = got == (y, w)
+        if not ok:
+            raise SystemExit(f"bench.py: open mismatch vs oracle expected value at 2^{log2n}")
+    ms = timed(lambda: prover.open(d_scal.data_ptr(), u, yw[:32], yw[32:]))
+    res[f"open_2^{log2n}"] = {"ms": ms, "opens_per_sec": 1e3 / ms, "verified_vs_oracle": ok,
+                              "what": "open_kzg (quotient scan + MSM of the quotient), coefficients resident, range-sharded x%d" % world}
+
+    # ---- C3: 2^20 commit + open over the N GPUs (own contexts: the SRS of a 2^20 setup, sharded N ways) ----
+    if log2n >= 20:
+        lg = 20
+        n3 = 1 << lg
+        lo3, hi3 = shard_range(n3, rank, world)
+        ctx3 = mz.Context(dev.index)
+        ctx3.srs_generate(alpha, hi3 - lo3, first=lo3)
+        ops3 = DeviceOps(ctx3, dev)
+        if world > 1 and ops.fused:
+            ops3.attach_peers(rank, world)
+        prover3 = ShardedKZG(ops3, rank, world, n3)
+        sc3 = synth.random_scalars(n3, synth.SEED_SCALARS + lg)
+        d3 = torch.from_numpy(sc3[lo3:hi3].view(np.int64).reshape(-1).copy()).to(dev)
+        c_out = torch.zeros(64, dtype=torch.uint8, device=dev)
+        prover3.commit(d3.data_ptr(), c_out)
+        prover3.open(d3.data_ptr(), u, yw[:32], yw[32:])
+        torch.cuda.synchronize()
+        got_c = mz.context.point_from_bytes(c_out.cpu().numpy().tobytes())
+        got_o = read_open()
+        ok = None
+        if not args.no_verify:
+            ec, y, w = expected(sc3, n3)
+            ok = got_c == ec and got_o == (y, w)
+            if not ok:
+                raise SystemExit("bench.py: C3 (2^20 commit + open) mismatch vs oracle expected values")
+        ms_c = timed(lambda: prover3.commit(d3.data_ptr(), c_out))
+        ms_o = timed(lambda: prover3.open(d3.data_ptr(), u, yw[:32], yw[32:]))
+
+        def both():
+            prover3.commit(d3.data_ptr(), c_out)
+            prover3.open(d3.data_ptr(), u, yw[:32], yw[32:])
+
+        ms_b = timed(both)
+        res["C3_commit_open_2^20"] = {"commit_ms": ms_c, "open_ms": ms_o, "commit_plus_open_ms": ms_b,
+                                      "commits_per_sec": 1e3 / ms_c, "points_per_sec": n3 / (ms_c * 1e-3),
+                                      "verified_vs_oracle": ok, "what": "coefficients resident, range-sharded x%d" % world}
+        # C2 on the way: 2^16 commit on ONE GPU (rank 0's context holds [0, 2^20 / N) >= 2^16 points)
+        if hi3 - lo3 >= (1 << 16) and rank == 0:
+            d2 = torch.from_numpy(sc3[: 1 << 16].view(np.int64).reshape(-1).copy()).to(dev)
+            ctx3.commit_dev(d2.data_ptr(), 1 << 16, c_out.data_ptr())
+            torch.cuda.synchronize()
+            got2 = mz.context.point_from_bytes(c_out.cpu().numpy().tobytes())
+            ok2 = None if args.no_verify else got2 == orc.fast_mul(oc.fr_eval_bytes(sc3[: 1 << 16].tobytes(), 1 << 16, alpha))
+            if ok2 is False:
+                raise SystemExit("bench.py: C2 (2^16 commit) mismatch")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                ctx3.commit_dev(d2.data_ptr(), 1 << 16, c_out.data_ptr())
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                ctx3.commit_dev(d2.data_ptr(), 1 << 16, c_out.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 10
+            res["C2_commit_2^16_one_gpu"] = {"commit_ms": ms2, "points_per_sec": (1 << 16) / (ms2 * 1e-3), "verified_vs_oracle": ok2}
+        barrier()
+
+        # ---- C5: Gemini fold + 21 commitments of a 2^20 multilinear, on rank 0 ----
+        if rank == 0:
+            ctx5 = ctx3 if world == 1 else mz.Context(dev.index)
+            if world > 1:
+                ctx5.srs_generate(alpha, n3)
+            pinned = ctx5.host_alloc(n3 * 32)
+            gc = synth.random_scalars(n3, synth.SEED_GEMINI_COEF)
+            pinned[:] = gc.view(np.uint8).reshape(-1)
+            coefs = pinned.reshape(n3, 32)
+            rhos = synth.limbs_to_ints(synth.random_scalars(lg, synth.SEED_GEMINI_RHO))
+            pts = ctx5.gemini_fold_commit(coefs, rhos)
+            ok = None
+            if not args.no_verify:
+                level, ln, exp = gc.tobytes(), n3, []
+                for i in range(lg + 1):
+                    exp.append(orc.fast_mul(oc.fr_eval_bytes(level, ln, alpha)))
+                    if i < lg:
+                        level = oc.fold_bytes(level, ln // 2, rhos[i])
+                        ln //= 2
+                ok = pts == exp
+                if not ok:
+                    raise SystemExit("bench.py: C5 (Gemini 2^20) commitments differ from the oracle's")
+            for _ in range(2):
+                ctx5.gemini_fold_commit(coefs, rhos)
+            times = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                ctx5.gemini_fold_commit(coefs, rhos)
+                times.append((time.perf_counter() - t0) * 1e3)
+            res["C5_gemini_2^20"] = {"fold_plus_21_commits_ms": min(times), "median_ms": sorted(times)[2], "verified_vs_oracle": ok,
+                                     "what": "host API call (32 MiB H2D of pinned coefficients and 21 x 64 B D2H inside), one GPU"}
+            ctx5.host_free(pinned)
+            if ctx5 is not ctx3:
+                ctx5.close()
+        barrier()
+        if world > 1 and ops3.fused:
+            ctx3.peer_detach()
+        ctx3.close()
+    return res
 
 
 def run_extras(ctx, mz, synth, torch, alpha, log2n):

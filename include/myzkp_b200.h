@@ -43,7 +43,17 @@ int myzkp_ctx_create(myzkp_ctx** out, int device_id);
 int myzkp_ctx_destroy(myzkp_ctx* ctx);
 /* Run all work of this ctx on an existing CUDA stream (cudaStream_t). */
 int myzkp_ctx_set_stream(myzkp_ctx* ctx, void* cuda_stream);
+/* Waits for the ctx stream.  Also reports what the asynchronous device-pointer calls could not: a scalar >= r
+ * seen since the last synchronising call (MYZKP_ERR_NONCANONICAL - the flag is sticky and cleared once reported)
+ * and a peer exchange that timed out (MYZKP_ERR_CUDA). */
 int myzkp_ctx_sync(myzkp_ctx* ctx);
+/* Size every scratch buffer for commits / opens / Gemini folds of up to n_max coefficients now (runs the
+ * pipelines once on zeros), so later calls allocate nothing.  Required before sharded calls on contexts that share
+ * ONE device with an attached peer (myzkp_peer_attach_local): there a later cudaMalloc would wait for the whole
+ * device, i.e. for a peer's exchange kernel that is itself waiting for this rank; such contexts therefore refuse to
+ * grow their scratch (MYZKP_ERR_CUDA with an explanatory message) instead of stalling.  Call again after
+ * myzkp_ctx_set_msm_params or a new SRS. */
+int myzkp_ctx_reserve(myzkp_ctx* ctx, size_t n_max);
 const char* myzkp_last_error(const myzkp_ctx* ctx);
 /* Number of this library's kernels launched by the ctx so far. */
 uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
@@ -59,8 +69,8 @@ int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds);
 /* Host-buffer commit/open upload a large polynomial in chunks on a copy stream while
  * earlier chunks are already being processed (each chunk is an MSM against its own SRS
  * range and the same window; the bucket sets are added and reduced once).  Chunk sizes grow
- * 4x so only the small first upload is exposed.  0 = automatic (1 below 2^22 coefficients,
- * 2 from 2^22, 3 from 2^24), 1..8 forces a chunk count. */
+ * 4x so only the small first upload is exposed.  0 = automatic (see upload_chunks() in csrc/capi.cu),
+ * 1..8 forces a chunk count. */
 int myzkp_ctx_set_upload_chunks(myzkp_ctx* ctx, int chunks);
 
 /* Per-phase CUDA-event timing of the MSM (events on the ctx stream, kept for the
@@ -76,7 +86,9 @@ int myzkp_host_alloc(void** out, size_t bytes);
 int myzkp_host_free(void* p);
 
 /* ---- SRS = PublicKeyKZG.powers_1 (kzg.rs:8-11, 27-40) ------------------- */
-/* Load n affine points.  Builds the resident table of 2^(8j) multiples. */
+/* Load n affine points.  Builds the resident table: row j holds 2^(b_j) P_i for the bit offsets b_j = multiples of
+ * 4 and of 22 (70 rows, windows c in {4, 8, 12, 16, 20, 22, 24}); a very large SRS falls back to multiples of 8
+ * (32 rows).  myzkp_srs_table_info reports what was built. */
 int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le /* n*64 */, size_t n);
 /* setup_kzg with the (unseeded, kzg.rs:28) alpha injected: points
  * [alpha^(first+i)]G for i < n; n = max_d + 1 (kzg.rs:32).  `first` lets a
@@ -91,6 +103,12 @@ int myzkp_srs_generate_g2(myzkp_ctx* ctx, const uint8_t alpha_le[32], const uint
                           size_t n, uint8_t* out /* n*128 */);
 int myzkp_srs_read_g1(myzkp_ctx* ctx, size_t off, size_t n, uint8_t* out /* n*64 */);
 size_t myzkp_srs_len(const myzkp_ctx* ctx);
+/* The resident table costs rows x 64 B per SRS point (70 rows by default = 70 GiB at 2^24 points on one GPU).
+ * window_mask (bit c set <=> MSM window c usable, 1 <= c <= 24; 0 = automatic) restricts the NEXT
+ * myzkp_srs_load_g1 / _generate_g1 to the rows those windows need - e.g. 1<<22 alone is 12 rows, (1<<16)|(1<<22)
+ * is 27.  The MSM then picks among the available windows only. */
+int myzkp_ctx_set_table_windows(myzkp_ctx* ctx, uint32_t window_mask);
+int myzkp_srs_table_info(const myzkp_ctx* ctx, int* out_rows, uint64_t* out_bytes, uint32_t* out_windows);
 
 /* ---- commit / open, host buffers --------------------------------------- */
 /* commit_kzg (kzg.rs:57-59) = Polynomial::eval_with_powers_on_curve
@@ -112,8 +130,9 @@ int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const si
  * NULL it receives the m folded polynomials back to back (2^(m-1) + ... + 1
  * coefficients, 32 B each). */
 int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_pow2,
-                             const uint8_t* rhos_le /* m*32 */, uint8_t* out /* (m+1)*64 */,
-                             uint8_t* out_folds /* (n_pow2-1)*32 or NULL */);
+                             const uint8_t* rhos_le /* n_rhos*32 */, size_t n_rhos /* must be m = log2 n_pow2:
+                             SplitFoldError::PointsLenMismatch otherwise (gemini.rs:60-66) */,
+                             uint8_t* out /* (m+1)*64 */, uint8_t* out_folds /* (n_pow2-1)*32 or NULL */);
 /* batch_open_kzg (kzg.rs:74-88): ys[i] = f(us[i]); W = commit((f - I)/Z) with I the
  * interpolant of (us, ys) and Z = prod (x - us[i]).  Since deg I < k the quotient is the
  * floor quotient of f by Z, computed as k successive (x - u_i) divisions.  k <= 64;
@@ -186,6 +205,9 @@ int myzkp_peer_set_timeout_ms(myzkp_ctx* ctx, uint32_t ms);
  * 64-byte commitment.  _dev: device pointers, asynchronous on the ctx stream. */
 int myzkp_kzg_commit_sharded_dev(myzkp_ctx* ctx, const void* d_scalars, size_t n_local, void* d_out_c64);
 int myzkp_kzg_commit_sharded(myzkp_ctx* ctx, const uint8_t* scalars_le, size_t n_local, uint8_t out_c[64]);
+/* open_kzg over the same sharding with this rank's coefficient slice in host memory; every rank ends with (y, W). */
+int myzkp_kzg_open_sharded(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_local, const uint8_t u_le[32],
+                           uint8_t out_y[32], uint8_t out_w[64]);
 /* the exchange + sum + affine kernel on its own: this rank's XYZZ partial (device) -> the sum over ranks */
 int myzkp_g1_exchange_sum_dev(myzkp_ctx* ctx, const void* d_partial_xyzz128, void* d_out_c64);
 /* open_kzg (kzg.rs:61-72) over the same sharding: range evaluation, exchange + carry composition,
@@ -205,6 +227,26 @@ int myzkp_fr_range_eval_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const
                             void* d_out_h32, void* d_out_upow32);
 int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
                                 const uint8_t carry_in_le[32], void* d_q /* n*32 */, void* d_c0 /* 32 */);
+
+/* ---- one process, several GPUs (csrc/multi.cu) ---------------------------------------------------------
+ * SURVEY 8(b)'s `myzkp_ctx_create(out, device_ids, n_dev)`: a multi-device context owns one myzkp_ctx and one host
+ * thread per listed device; the SRS is range-sharded over them (contiguous ceil-split), commit / open hand every
+ * device its coefficient slice and finish in the peer-memory exchange kernel.  Nothing but this library is on the
+ * path (no torch.distributed, no NCCL) - it is what a single-process Rust host drives (kzg.rs:57-72).  A device id
+ * may be listed more than once (several ranks on one GPU: used by the single-GPU tests). */
+typedef struct myzkp_mctx myzkp_mctx;
+int myzkp_device_count(void); /* usable CUDA devices (0 when there is none) */
+int myzkp_mctx_create(myzkp_mctx** out, const int* device_ids, int n_dev);
+int myzkp_mctx_destroy(myzkp_mctx* m);
+const char* myzkp_mctx_last_error(const myzkp_mctx* m);
+int myzkp_mctx_world(const myzkp_mctx* m);
+myzkp_ctx* myzkp_mctx_rank(myzkp_mctx* m, int g); /* the per-device context (owned by m) */
+size_t myzkp_mctx_srs_len(const myzkp_mctx* m);
+int myzkp_mctx_srs_generate_g1(myzkp_mctx* m, const uint8_t alpha_le[32], size_t n);
+int myzkp_mctx_srs_load_g1(myzkp_mctx* m, const uint8_t* affine_xy_le /* n*64 */, size_t n);
+int myzkp_mctx_kzg_commit(myzkp_mctx* m, const uint8_t* coefs_le /* n*32 */, size_t n, uint8_t out_c[64]);
+int myzkp_mctx_kzg_open(myzkp_mctx* m, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32],
+                        uint8_t out_w[64]);
 
 /* ---- test hooks: batched field / group ops for parity tests -------------
  * op: 0 add, 1 sub, 2 mul, 3 inverse(a) (Fermat), 4 neg(a), 5 inverse(a) (binary GCD);

@@ -186,6 +186,8 @@ inline void setup_kzg_range(PublicKeyKZG& pk, size_t first, size_t count, const 
 inline void attach_peers(const std::vector<PublicKeyKZG*>& ranks) {
   std::vector<myzkp_ctx*> ctxs;
   for (auto* r : ranks) {
+    // size the scratch now: ranks sharing a device must not allocate once a peer may be spinning in an exchange
+    r->check(myzkp_ctx_reserve(r->ctx(), myzkp_srs_len(r->ctx())));
     r->check(myzkp_peer_export(r->ctx(), nullptr));
     ctxs.push_back(r->ctx());
   }
@@ -200,5 +202,44 @@ inline CommitmentKZG commit_kzg_sharded(const Polynomial& local_slice, const Pub
                                     local_slice.coef.size(), c.xy.data()));
   return c;
 }
+
+inline ProofKZG open_kzg_sharded(const Polynomial& local_slice, const Scalar& u, const PublicKeyKZG& pk) {
+  ProofKZG pr;
+  pk.check(myzkp_kzg_open_sharded(pk.ctx(), local_slice.coef.empty() ? nullptr : local_slice.coef[0].data(),
+                                  local_slice.coef.size(), u.data(), pr.y.data(), pr.w.xy.data()));
+  return pr;
+}
+
+// ---- one host thread, several GPUs: the multi-device context (csrc/multi.cu) ----
+class MultiGpuKZG {
+ public:
+  explicit MultiGpuKZG(const std::vector<int>& devices) {
+    if (myzkp_mctx_create(&m_, devices.data(), (int)devices.size()) != MYZKP_OK)
+      throw std::runtime_error("myzkp_b200: cannot create contexts on the listed devices (there is no CPU fallback)");
+  }
+  ~MultiGpuKZG() { myzkp_mctx_destroy(m_); }
+  MultiGpuKZG(const MultiGpuKZG&) = delete;
+  MultiGpuKZG& operator=(const MultiGpuKZG&) = delete;
+  void check(int code) const {
+    if (code != MYZKP_OK) throw std::runtime_error(std::string("myzkp_b200: ") + myzkp_mctx_last_error(m_));
+  }
+  void setup(size_t max_d, const Scalar& alpha) { check(myzkp_mctx_srs_generate_g1(m_, alpha.data(), max_d + 1)); }
+  size_t size() const { return myzkp_mctx_srs_len(m_); }
+  int world() const { return myzkp_mctx_world(m_); }
+  CommitmentKZG commit_kzg(const Polynomial& f) const {
+    G1Point c;
+    check(myzkp_mctx_kzg_commit(m_, f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(), c.xy.data()));
+    return c;
+  }
+  ProofKZG open_kzg(const Polynomial& f, const Scalar& u) const {
+    ProofKZG pr;
+    check(myzkp_mctx_kzg_open(m_, f.coef.empty() ? nullptr : f.coef[0].data(), f.coef.size(), u.data(), pr.y.data(),
+                              pr.w.xy.data()));
+    return pr;
+  }
+
+ private:
+  myzkp_mctx* m_ = nullptr;
+};
 
 }  // namespace myzkp_b200

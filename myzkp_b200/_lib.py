@@ -22,6 +22,7 @@ SIGNATURES = {
     "myzkp_ctx_destroy": (_i, [_vp]),
     "myzkp_ctx_set_stream": (_i, [_vp, _vp]),
     "myzkp_ctx_sync": (_i, [_vp]),
+    "myzkp_ctx_reserve": (_i, [_vp, _sz]),
     "myzkp_last_error": (_c.c_char_p, [_vp]),
     "myzkp_kernel_launches": (_c.c_uint64, [_vp]),
     "myzkp_ctx_set_msm_params": (_i, [_vp, _i, _i]),
@@ -39,10 +40,12 @@ SIGNATURES = {
     "myzkp_pairing": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "myzkp_pairing_product_is_one": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "myzkp_srs_len": (_sz, [_vp]),
+    "myzkp_ctx_set_table_windows": (_i, [_vp, _c.c_uint32]),
+    "myzkp_srs_table_info": (_i, [_vp, _c.POINTER(_i), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint32)]),
     "myzkp_kzg_commit": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_kzg_open": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_kzg_commit_batch": (_i, [_vp, _c.POINTER(_vp), _c.POINTER(_sz), _sz, _vp]),
-    "myzkp_gemini_fold_commit": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "myzkp_gemini_fold_commit": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "myzkp_kzg_batch_open": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "myzkp_kzg_prove_degree_bound": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "myzkp_g1_msm": (_i, [_vp, _vp, _vp, _sz, _vp]),
@@ -61,6 +64,18 @@ SIGNATURES = {
     "myzkp_g1_exchange_sum_dev": (_i, [_vp, _vp, _vp]),
     "myzkp_kzg_commit_sharded": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_kzg_open_sharded_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "myzkp_kzg_open_sharded": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "myzkp_device_count": (_i, []),
+    "myzkp_mctx_create": (_i, [_c.POINTER(_vp), _c.POINTER(_i), _i]),
+    "myzkp_mctx_destroy": (_i, [_vp]),
+    "myzkp_mctx_last_error": (_c.c_char_p, [_vp]),
+    "myzkp_mctx_world": (_i, [_vp]),
+    "myzkp_mctx_rank": (_vp, [_vp, _i]),
+    "myzkp_mctx_srs_len": (_sz, [_vp]),
+    "myzkp_mctx_srs_generate_g1": (_i, [_vp, _vp, _sz]),
+    "myzkp_mctx_srs_load_g1": (_i, [_vp, _vp, _sz]),
+    "myzkp_mctx_kzg_commit": (_i, [_vp, _vp, _sz, _vp]),
+    "myzkp_mctx_kzg_open": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_g1_sum_partials_dev": (_i, [_vp, _vp, _sz, _vp]),
     "myzkp_fr_range_eval_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "myzkp_fr_range_quotient_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),

@@ -93,7 +93,26 @@ class Context:
         self._ck(self._lib.myzkp_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
 
     def sync(self):
+        """Waits for the ctx stream; raises for a non-canonical scalar seen by an asynchronous device-pointer call
+        since the last synchronising call, or for a peer exchange that timed out."""
         self._ck(self._lib.myzkp_ctx_sync(self.h))
+
+    def reserve(self, n_max: int):
+        """Size all scratch for commits / opens of up to n_max coefficients now (needed before sharded calls when
+        several ranks share one device)."""
+        self._ck(self._lib.myzkp_ctx_reserve(self.h, int(n_max)))
+
+    def set_table_windows(self, windows=()):
+        """Restrict the next SRS table to the rows the given MSM windows need (() = automatic, 70 rows)."""
+        mask = 0
+        for c in windows:
+            mask |= 1 << int(c)
+        self._ck(self._lib.myzkp_ctx_set_table_windows(self.h, mask))
+
+    def table_info(self):
+        rows, nbytes, win = ctypes.c_int(0), ctypes.c_uint64(0), ctypes.c_uint32(0)
+        self._ck(self._lib.myzkp_srs_table_info(self.h, ctypes.byref(rows), ctypes.byref(nbytes), ctypes.byref(win)))
+        return {"rows": rows.value, "bytes": nbytes.value, "windows": [c for c in range(1, 25) if (win.value >> c) & 1]}
 
     def set_msm_params(self, window_bits: int = 0, segment_len: int = 0):
         self._ck(self._lib.myzkp_ctx_set_msm_params(self.h, window_bits, segment_len))
@@ -282,7 +301,7 @@ class Context:
         folds = np.zeros((max(n - 1, 0), 32), np.uint8) if want_folds else None
         self._ck(
             self._lib.myzkp_gemini_fold_commit(
-                self.h, _ptr(a), n, _ptr(r) if m else None, _ptr(out), _ptr(folds) if want_folds and n > 1 else None
+                self.h, _ptr(a), n, _ptr(r) if m else None, m, _ptr(out), _ptr(folds) if want_folds and n > 1 else None
             )
         )
         pts = [point_from_bytes(out[i]) for i in range(m + 1)]
@@ -384,10 +403,99 @@ def _dev_methods():
         self._ck(self._lib.myzkp_kzg_open_sharded_dev(self.h, ctypes.c_void_p(d_coefs), n_local, _ptr(ub),
                                                       ctypes.c_void_p(d_out_y32), ctypes.c_void_p(d_out_w64)))
 
+    def open_sharded(self, coefs: np.ndarray, u: int):
+        """Host coefficients of this rank's range -> (y, W) of the whole polynomial (synchronous)."""
+        a = scalars_to_bytes(coefs)
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        y = np.zeros(32, np.uint8)
+        w = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_kzg_open_sharded(self.h, _ptr(a), a.shape[0], _ptr(ub), _ptr(y), _ptr(w)))
+        return bytes_to_int(y), point_from_bytes(w)
+
     for f in (commit_dev, open_dev, msm_partial_dev, msm_partial_host, sum_partials_dev, fr_range_eval_dev, fr_range_quotient_dev,
               peer_export, peer_attach, peer_attach_local, peer_detach, peer_set_timeout_ms, commit_sharded_dev,
-              exchange_sum_dev, commit_sharded, open_sharded_dev):
+              exchange_sum_dev, commit_sharded, open_sharded_dev, open_sharded):
         setattr(Context, f.__name__, f)
 
 
 _dev_methods()
+
+
+class _RankView(Context):
+    """A rank of a MultiContext: same methods as Context, but the handle is owned by the multi-device context."""
+
+    def __init__(self, lib, handle, device):
+        self._lib = lib
+        self.h = ctypes.c_void_p(handle)
+        self.device = device
+
+    def close(self):
+        self.h = None
+
+
+class MultiContext:
+    """One process driving several GPUs through the C ABI alone (csrc/multi.cu): the SRS is range-sharded over the
+    listed devices, commit / open hand every device its coefficient slice and finish in the peer-memory exchange
+    kernel.  No torch.distributed, no NCCL.  A device may be listed more than once (ranks sharing a GPU)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _lib.load()
+        ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        code = self._lib.myzkp_mctx_create(ctypes.byref(h), ids, len(devices))
+        if code != 0:
+            raise _lib.MyzkpError(code, f"cannot create contexts on devices {list(devices)} (no CPU fallback exists)")
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.myzkp_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, code):
+        if code != 0:
+            msg = self._lib.myzkp_mctx_last_error(self.h)
+            raise _lib.MyzkpError(code, msg.decode() if msg else "")
+
+    @property
+    def world(self) -> int:
+        return int(self._lib.myzkp_mctx_world(self.h))
+
+    @property
+    def srs_len(self) -> int:
+        return int(self._lib.myzkp_mctx_srs_len(self.h))
+
+    def rank(self, g: int) -> Context:
+        return _RankView(self._lib, self._lib.myzkp_mctx_rank(self.h, g), self.devices[g])
+
+    def srs_generate(self, alpha: int, n: int):
+        a = np.frombuffer(int(alpha % R_MOD).to_bytes(32, "little"), dtype=np.uint8).copy()
+        self._ck(self._lib.myzkp_mctx_srs_generate_g1(self.h, _ptr(a), n))
+
+    def srs_load(self, points):
+        if isinstance(points, np.ndarray):
+            a = np.ascontiguousarray(points, dtype=np.uint8).reshape(-1, 64)
+        else:
+            a = np.frombuffer(b"".join(point_to_bytes(p) for p in points), dtype=np.uint8).reshape(-1, 64).copy()
+        self._ck(self._lib.myzkp_mctx_srs_load_g1(self.h, _ptr(a), a.shape[0]))
+
+    def commit(self, coefs):
+        a = scalars_to_bytes(coefs)
+        out = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_mctx_kzg_commit(self.h, _ptr(a), a.shape[0], _ptr(out)))
+        return point_from_bytes(out)
+
+    def open(self, coefs, u: int):
+        a = scalars_to_bytes(coefs)
+        ub = np.frombuffer(int(u).to_bytes(32, "little"), dtype=np.uint8).copy()
+        y = np.zeros(32, np.uint8)
+        w = np.zeros(64, np.uint8)
+        self._ck(self._lib.myzkp_mctx_kzg_open(self.h, _ptr(a), a.shape[0], _ptr(ub), _ptr(y), _ptr(w)))
+        return bytes_to_int(y), point_from_bytes(w)

@@ -27,10 +27,16 @@ constexpr size_t kSmallY = 640;       // 32 B: y / c0
 constexpr size_t kSmallXyzz = 1024;   // XYZZ result(s): up to 16 slots (2 KiB)
 constexpr size_t kSmallPoint = 3072;  // 64 B affine bytes result
 
+// The non-canonical flag is STICKY: kernels only ever OR into it, begin_call does not clear it, and it is read
+// (and then cleared) by whichever comes first - the end of a host-buffer call or myzkp_ctx_sync.  So an
+// asynchronous device-pointer call with a scalar >= r is reported by the next synchronising call.
 int begin_call(myzkp_ctx* ctx) {
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
-  MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->small.as<uint8_t>() + kSmallFlag, 0, sizeof(int), ctx->stream));
+  if (!ctx->small_init) {
+    MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->small.as<uint8_t>() + kSmallFlag, 0, sizeof(int), ctx->stream));
+    ctx->small_init = true;
+  }
   return MYZKP_OK;
 }
 
@@ -82,21 +88,21 @@ int enqueue_chunk_uploads(myzkp_ctx* ctx, const uint8_t* host, uint8_t* dev, siz
 
 int end_call_check_flag(myzkp_ctx* ctx) {
   int h_flag = 0;
-  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, ctx->small.as<uint8_t>() + kSmallFlag, sizeof(int), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+  if (ctx->small_init)
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, ctx->small.as<uint8_t>() + kSmallFlag, sizeof(int), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
   MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h_flag) return fail(ctx, MYZKP_ERR_NONCANONICAL, "input scalar >= r (callers must sanitize, field.rs:260-270)");
+  if (h_flag) {
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->small.as<uint8_t>() + kSmallFlag, 0, sizeof(int), ctx->stream));
+    return fail(ctx, MYZKP_ERR_NONCANONICAL, "input scalar >= r (callers must sanitize, field.rs:260-270)");
+  }
   return MYZKP_OK;
 }
 
 constexpr int kMaxChildren = 8;
 
 void free_ctx_scratch(myzkp_ctx* ctx) {
-  DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
-                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
-                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
-  for (DevBuf* b : bufs) b->release();
+  for_each_scratch(ctx, [](DevBuf* b) { b->release(); });
 }
 
 // child i of ctx, (re)pointed at the parent's current SRS table
@@ -192,8 +198,46 @@ int myzkp_ctx_create(myzkp_ctx** out, int device_id) {
     return MYZKP_ERR_CUDA;
   }
   ctx->own_stream = true;
+  for_each_scratch(ctx, [ctx](DevBuf* b) { b->frozen = &ctx->peer_same_device; });
   *out = ctx;
   return MYZKP_OK;
+}
+
+int myzkp_ctx_reserve(myzkp_ctx* ctx, size_t n_max) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  MZ_TRY(begin_call(ctx));
+  // Run the pipelines once on all-zero coefficients: buffer sizes depend on the length only (window, entries,
+  // segments, tiles), so this sizes every scratch buffer exactly as a real commit / open of n_max would.
+  const bool was_frozen = ctx->peer_same_device;
+  ctx->peer_same_device = false;
+  int rc = MYZKP_OK;
+  auto run = [&]() -> int {
+    const size_t n = n_max ? n_max : 1;
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(2 * n * 32 + 32 * 66));  // Gemini keeps all levels and the challenges here
+    MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
+    MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure(66 * (sizeof(XYZZ) + 64)));
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.p, 0, n * 32, ctx->stream));
+    uint8_t* s = ctx->small.as<uint8_t>();
+    const uint8_t zero[32] = {0};
+    const size_t n_msm = n_max < ctx->srs_n ? n_max : ctx->srs_n;
+    if (ctx->table && n_msm) {
+      // twice the buckets: the chunked upload pipeline accumulates into a second set
+      MZ_CUDA_TRY(ctx, ctx->buckets.ensure(2 * ((size_t)1 << (msm_pick_window(ctx, n_msm) - 1)) * sizeof(XYZZ)));
+      MZ_TRY(msm_xyzz(ctx, ctx->scalars.as<uint32_t>(), n_msm, 0, reinterpret_cast<XYZZ*>(s + kSmallXyzz)));
+    }
+    if (n_max) {
+      MZ_TRY(fr_range_eval(ctx, ctx->scalars.as<uint32_t>(), n_max, zero, reinterpret_cast<uint32_t*>(s + kSmallY),
+                           reinterpret_cast<uint32_t*>(s + kSmallY + 32)));
+      MZ_TRY(fr_range_quotient(ctx, ctx->scalars.as<uint32_t>(), n_max, zero, nullptr, ctx->scalars2.as<uint32_t>(),
+                               reinterpret_cast<uint32_t*>(s + kSmallY)));
+    }
+    MZ_TRY(ensure_copy_stream(ctx));
+    MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MYZKP_OK;
+  };
+  rc = run();
+  ctx->peer_same_device = was_frozen;
+  return rc;
 }
 
 int myzkp_ctx_destroy(myzkp_ctx* ctx) {
@@ -240,7 +284,8 @@ int myzkp_ctx_set_stream(myzkp_ctx* ctx, void* cuda_stream) {
 int myzkp_ctx_sync(myzkp_ctx* ctx) {
   if (!ctx) return MYZKP_ERR_INVALID_ARG;
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  // reports (and clears) the sticky non-canonical flag of the asynchronous device-pointer calls
+  MZ_TRY(end_call_check_flag(ctx));
   return peer_check(ctx);
 }
 
@@ -371,6 +416,24 @@ int myzkp_kzg_open_sharded_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n_loc
   // q_{lo+i} pairs with local SRS point i (the global top quotient coefficient is the zero carry)
   MZ_TRY(msm_xyzz(ctx, ctx->scalars2.as<uint32_t>(), n_local, 0, res));
   return peer_exchange(ctx, 0, res, 160, d_out_w64, d_out_y32);
+}
+
+int myzkp_kzg_open_sharded(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_local, const uint8_t u_le[32],
+                           uint8_t out_y[32], uint8_t out_w[64]) {
+  if (!ctx || (!coefs_le && n_local) || !u_le || !out_y || !out_w) return MYZKP_ERR_INVALID_ARG;
+  if (n_local > ctx->srs_n) return fail(ctx, MYZKP_ERR_INVALID_ARG, "coefficient slice longer than this rank's SRS range");
+  MZ_TRY(begin_call(ctx));
+  if (n_local) {
+    MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n_local * 32));
+    MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n_local * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  uint8_t* s = ctx->small.as<uint8_t>();
+  // results land behind the scan's own use of kSmallY (pair, carry): y at +128, W at kSmallPoint
+  MZ_TRY(myzkp_kzg_open_sharded_dev(ctx, ctx->scalars.p, n_local, u_le, s + kSmallY + 128, s + kSmallPoint));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY + 128, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_w, s + kSmallPoint, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_TRY(end_call_check_flag(ctx));
+  return peer_check(ctx);
 }
 
 int myzkp_g1_sum_partials_dev(myzkp_ctx* ctx, const void* d_partials, size_t k, void* d_out_c64) {
@@ -559,12 +622,14 @@ int myzkp_kzg_commit_batch(myzkp_ctx* ctx, const uint8_t* const* coefs, const si
 }
 
 int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_pow2, const uint8_t* rhos_le,
-                             uint8_t* out, uint8_t* out_folds) {
+                             size_t n_rhos, uint8_t* out, uint8_t* out_folds) {
   if (!ctx || !coefs_le || !out) return MYZKP_ERR_INVALID_ARG;
   if (n_pow2 == 0 || (n_pow2 & (n_pow2 - 1)))
     return fail(ctx, MYZKP_ERR_INVALID_ARG, "coefs.len() must be a power of two (gemini.rs:55-57)");
   int m = 0;
   while (((size_t)1 << m) < n_pow2) m++;
+  if (n_rhos != (size_t)m)
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "points.len() must be log2(coefs.len()) (SplitFoldError::PointsLenMismatch, gemini.rs:60-66)");
   if (m && !rhos_le) return MYZKP_ERR_INVALID_ARG;
   if (n_pow2 > ctx->srs_n) return fail(ctx, !ctx->table ? MYZKP_ERR_NO_SRS : MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS");
   for (int i = 0; i < m; i++)
@@ -612,25 +677,37 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
     }
   }
   myzkp_ctx* ch = nullptr;
+  int rc_child = MYZKP_OK, rc_parent = MYZKP_OK;
+  bool child_launched = false;
   if (!small_levels.empty()) {
     MZ_TRY(get_child(ctx, 0, &ch));
     MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, ctx->fork_ev, 0));  // the folds come first
-    int rc = msm_batch_xyzz(ch, small_levels.data(), small_levels.size(), 0, res + first_small);
-    if (rc != MYZKP_OK) return fail(ctx, rc, ch->err.c_str());
+    child_launched = true;
+    rc_child = msm_batch_xyzz(ch, small_levels.data(), small_levels.size(), 0, res + first_small);
     ctx->launches += ch->launches;
     ch->launches = 0;
-    MZ_CUDA_TRY(ctx, cudaEventRecord(ch->join_ev, ch->stream));
   }
-  {
+  if (rc_child == MYZKP_OK) {
     uint32_t* cur = base;
     size_t len = n_pow2;
-    for (int lvl = 0; lvl < first_small; lvl++) {
-      MZ_TRY(msm_xyzz(ctx, cur, len, 0, res + lvl));
+    for (int lvl = 0; lvl < first_small && rc_parent == MYZKP_OK; lvl++) {
+      rc_parent = msm_xyzz(ctx, cur, len, 0, res + lvl);
       cur += len * 8;
       len /= 2;
     }
   }
-  if (ch) MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0));
+  // join: whatever was enqueued on the child reads `base` and writes `res`, so the parent stream waits for it on
+  // every path out of here, error paths included
+  if (child_launched) {
+    cudaError_t je = cudaEventRecord(ch->join_ev, ch->stream);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0);
+    if (je != cudaSuccess) {
+      cudaStreamSynchronize(ch->stream);
+      cudaGetLastError();
+    }
+  }
+  if (rc_child != MYZKP_OK) return fail(ctx, rc_child, ch->err.c_str());
+  if (rc_parent != MYZKP_OK) return rc_parent;
   MZ_TRY(xyzz_to_bytes(ctx, res, (size_t)(m + 1), d_pts));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pts, (size_t)(m + 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_folds && n_pow2 > 1)

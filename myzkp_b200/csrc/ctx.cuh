@@ -22,8 +22,13 @@ constexpr int kMaxTableRows = 80;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  // When set and true, the buffer must not grow: cudaMalloc / cudaFree synchronise the whole device, and with
+  // several ranks on ONE device (in-process tests) that would wait for a peer's exchange kernel which is itself
+  // spinning for this rank - see myzkp_ctx_reserve.
+  const bool* frozen = nullptr;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    if (frozen && *frozen) return cudaErrorNotPermitted;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -73,6 +78,7 @@ struct myzkp_ctx {
   int row_bits[mz::kMaxTableRows] = {};   // sorted bit offsets of the rows
   uint8_t row_of_bit[256] = {};           // bit offset -> row (0xff = absent)
   uint32_t windows = 0;                   // bit c set <=> window c is supported
+  uint32_t table_windows = 0;             // caller-chosen window set for the next SRS (0 = automatic)
   uint8_t* d_row_of_bit = nullptr;        // device copies
   int* d_row_bits = nullptr;
 
@@ -91,6 +97,7 @@ struct myzkp_ctx {
   mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
+  bool small_init = false; // the sticky non-canonical flag inside `small` has been zeroed once
   mz::DevBuf descs;        // per-polynomial descriptors of a batched MSM
   mz::DevBuf xyzz_tmp;     // XYZZ temporaries (SRS generation)
   // host-API upload pipeline: chunks of a large polynomial are copied on copy_stream
@@ -107,6 +114,7 @@ struct myzkp_ctx {
   uint8_t* peer_bufs[kMaxPeers] = {};
   bool peer_ipc[kMaxPeers] = {};
   int peer_rank = -1, peer_world = 0;
+  bool peer_same_device = false;  // some attached peer shares this device: scratch is frozen (DevBuf::frozen)
   uint32_t peer_epoch = 0;
   unsigned long long peer_timeout_ns = 10ull * 1000 * 1000 * 1000;
 
@@ -123,11 +131,25 @@ struct myzkp_ctx {
   uint64_t msm_info[kPhaseSlots][6] = {};
 };
 
+namespace mz {
+template <class F>
+inline void for_each_scratch(myzkp_ctx* ctx, F f) {
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
+                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
+  for (DevBuf* b : bufs) f(b);
+}
+}  // namespace mz
+
 #define MZ_CUDA_TRY(ctx, expr)                                                        \
   do {                                                                                \
     cudaError_t _e = (expr);                                                          \
     if (_e != cudaSuccess) {                                                          \
       (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+      if (_e == cudaErrorNotPermitted)                                                \
+        (ctx)->err += " - scratch would have to grow while peers on the same device are attached "  \
+                      "(a device-wide synchronisation could deadlock their exchange): call myzkp_ctx_reserve first"; \
       return (_e == cudaErrorMemoryAllocation) ? MYZKP_ERR_OOM : MYZKP_ERR_CUDA;      \
     }                                                                                 \
   } while (0)

@@ -167,6 +167,7 @@ static void peer_close(myzkp_ctx* ctx) {
   }
   ctx->peer_world = 0;
   ctx->peer_rank = -1;
+  ctx->peer_same_device = false;
 }
 
 void peer_release(myzkp_ctx* ctx) {
@@ -247,6 +248,9 @@ int myzkp_peer_attach_local(myzkp_ctx* ctx, int rank, int world, myzkp_ctx* cons
       cudaGetLastError();
     }
     ctx->peer_bufs[r] = ctxs[r]->peer_local;
+    // Ranks sharing one device (in-process tests): from now on this ctx's scratch must not grow - cudaMalloc /
+    // cudaFree wait for the whole device, i.e. for a peer's exchange kernel that is spinning for this very rank.
+    if (r != rank && ctxs[r]->device == ctx->device) ctx->peer_same_device = true;
   }
   ctx->peer_rank = rank;
   ctx->peer_world = world;

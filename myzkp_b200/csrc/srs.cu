@@ -201,6 +201,7 @@ int srs_alloc(myzkp_ctx* ctx, size_t n) {
   if ((uint64_t)n * ctx->table_rows >= (1ull << 31) ||
       (double)n * ctx->table_rows * sizeof(Affine) > 0.55 * (double)free_b)
     plan_rows(ctx, lean);
+  if (ctx->table_windows) plan_rows(ctx, ctx->table_windows);  // caller's choice (myzkp_ctx_set_table_windows)
   if ((uint64_t)n * ctx->table_rows >= (1ull << 31)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "SRS too large (n * rows must be < 2^31)");
   if (!ctx->d_row_of_bit) {
     MZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_row_of_bit, 256));
@@ -253,14 +254,26 @@ static int ensure_gcomb(myzkp_ctx* ctx) {
 
 using namespace mz;
 
+namespace {
+// Loading / generating an SRS is set-up work (it allocates the table anyway, which synchronises the device): the
+// scratch freeze of same-device peers (DevBuf::frozen) is lifted for its duration.
+struct SetupScope {
+  myzkp_ctx* ctx;
+  bool was;
+  explicit SetupScope(myzkp_ctx* c) : ctx(c), was(c->peer_same_device) { c->peer_same_device = false; }
+  ~SetupScope() { ctx->peer_same_device = was; }
+};
+}  // namespace
+
 extern "C" int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le, size_t n) {
   if (!ctx || (!affine_xy_le && n)) return MYZKP_ERR_INVALID_ARG;
+  SetupScope setup(ctx);
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   MZ_TRY(srs_alloc(ctx, n));
   if (n == 0) return MYZKP_OK;
   MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 64));
   MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
-  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 512);
+  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 528);  // own word: 512 is the sticky scalar flag
   MZ_CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, affine_xy_le, n * 64, cudaMemcpyHostToDevice, ctx->stream));
   srs_import<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->table, flag);
@@ -278,6 +291,7 @@ extern "C" int myzkp_srs_load_g1(myzkp_ctx* ctx, const uint8_t* affine_xy_le, si
 
 extern "C" int myzkp_srs_generate_g1(myzkp_ctx* ctx, const uint8_t alpha_le[32], size_t first, size_t n) {
   if (!ctx || !alpha_le) return MYZKP_ERR_INVALID_ARG;
+  SetupScope setup(ctx);
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   MZ_TRY(ensure_gcomb(ctx));
   MZ_TRY(srs_alloc(ctx, n));
@@ -321,3 +335,28 @@ extern "C" int myzkp_srs_read_g1(myzkp_ctx* ctx, size_t off, size_t n, uint8_t* 
 }
 
 extern "C" size_t myzkp_srs_len(const myzkp_ctx* ctx) { return ctx ? ctx->srs_n : 0; }
+
+extern "C" int myzkp_ctx_set_table_windows(myzkp_ctx* ctx, uint32_t window_mask) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  // bit c set <=> window c is to be supported; 1 <= c <= 24; the row count must fit kMaxTableRows
+  if (window_mask & ~0x01fffffeu) return fail(ctx, MYZKP_ERR_INVALID_ARG, "windows are 1..24 bits");
+  if (window_mask) {
+    bool used[256] = {};
+    int rows = 0;
+    for (int c = 1; c <= 24; c++)
+      if ((window_mask >> c) & 1)
+        for (int w = 0; w < (255 + c - 1) / c; w++)
+          if (!used[c * w]) { used[c * w] = true; rows++; }
+    if (rows > kMaxTableRows) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window set needs too many table rows");
+  }
+  ctx->table_windows = window_mask;
+  return MYZKP_OK;
+}
+
+extern "C" int myzkp_srs_table_info(const myzkp_ctx* ctx, int* out_rows, uint64_t* out_bytes, uint32_t* out_windows) {
+  if (!ctx) return MYZKP_ERR_INVALID_ARG;
+  if (out_rows) *out_rows = ctx->table ? ctx->table_rows : 0;
+  if (out_bytes) *out_bytes = ctx->table ? (uint64_t)ctx->srs_n * ctx->table_rows * sizeof(Affine) : 0;
+  if (out_windows) *out_windows = ctx->table ? ctx->windows : 0;
+  return MYZKP_OK;
+}

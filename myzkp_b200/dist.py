@@ -59,6 +59,9 @@ class DeviceOps:
     def __init__(self, ctx, device: torch.device):
         self.ctx = ctx
         self.device = device
+        # everything below mixes library calls with torch collectives and .cpu() reads on torch's current stream:
+        # put the library on that stream so the two are ordered (the library's default is a private stream)
+        ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
         self.partial = torch.zeros(128, dtype=torch.uint8, device=device)
         self.pair = torch.zeros(64, dtype=torch.uint8, device=device)  # (h, u^n)
         self.c0 = torch.zeros(32, dtype=torch.uint8, device=device)
@@ -97,6 +100,10 @@ class DeviceOps:
 
     def open_fused(self, d_coefs: int, n: int, u: int, out_y32: torch.Tensor, out_w64: torch.Tensor) -> None:
         self.ctx.open_sharded_dev(d_coefs, n, u, out_y32.data_ptr(), out_w64.data_ptr())
+
+    def open_single(self, d_coefs: int, n: int, u: int, out_y32: torch.Tensor, out_w64: torch.Tensor) -> None:
+        """world_size 1: the plain single-GPU open (one scan, no exchange, no host round trip)."""
+        self.ctx.open_dev(d_coefs, n, u, out_y32.data_ptr(), out_w64.data_ptr())
 
     def msm_partial(self, d_scalars: int, n: int) -> torch.Tensor:
         self.ctx.msm_partial_dev(d_scalars, n, 0, self.partial.data_ptr())
@@ -161,6 +168,8 @@ class ShardedKZG:
         """open_kzg over the sharded polynomial: every rank ends with (y, W)."""
         if getattr(self.ops, "fused", False):
             return self.ops.open_fused(d_coefs_local, self.n_local, u, out_y32, out_w64)
+        if self.world == 1 and hasattr(self.ops, "open_single"):
+            return self.ops.open_single(d_coefs_local, self.n_local, u, out_y32, out_w64)
         pair = self.ops.range_eval(d_coefs_local, self.n_local, u)
         g = self._all_gather(pair, "_gather64").cpu().numpy().tobytes()
         hs = [int.from_bytes(g[64 * r : 64 * r + 32], "little") for r in range(self.world)]

@@ -6,6 +6,11 @@ use std::os::raw::{c_char, c_int, c_void};
 pub struct myzkp_ctx {
     _private: [u8; 0],
 }
+/// one process, several GPUs (csrc/multi.cu)
+#[repr(C)]
+pub struct myzkp_mctx {
+    _private: [u8; 0],
+}
 
 pub const MYZKP_OK: c_int = 0;
 pub const MYZKP_ERR_INVALID_ARG: c_int = -1;
@@ -19,6 +24,7 @@ extern "C" {
     pub fn myzkp_ctx_destroy(ctx: *mut myzkp_ctx) -> c_int;
     pub fn myzkp_ctx_set_stream(ctx: *mut myzkp_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn myzkp_ctx_sync(ctx: *mut myzkp_ctx) -> c_int;
+    pub fn myzkp_ctx_reserve(ctx: *mut myzkp_ctx, n_max: usize) -> c_int;
     pub fn myzkp_last_error(ctx: *const myzkp_ctx) -> *const c_char;
     pub fn myzkp_kernel_launches(ctx: *const myzkp_ctx) -> u64;
     pub fn myzkp_ctx_set_msm_params(ctx: *mut myzkp_ctx, window_bits: c_int, segment_len: c_int) -> c_int;
@@ -35,6 +41,8 @@ extern "C" {
     pub fn myzkp_srs_generate_g2(ctx: *mut myzkp_ctx, alpha_le: *const u8, base_or_null: *const u8, first: usize, n: usize,
                                  out: *mut u8) -> c_int;
     pub fn myzkp_srs_len(ctx: *const myzkp_ctx) -> usize;
+    pub fn myzkp_ctx_set_table_windows(ctx: *mut myzkp_ctx, window_mask: u32) -> c_int;
+    pub fn myzkp_srs_table_info(ctx: *const myzkp_ctx, out_rows: *mut c_int, out_bytes: *mut u64, out_windows: *mut u32) -> c_int;
     pub fn myzkp_pairing(ctx: *mut myzkp_ctx, g1: *const u8, g2: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn myzkp_pairing_product_is_one(ctx: *mut myzkp_ctx, g1: *const u8, g2: *const u8, n: usize, out_is_one: *mut c_int) -> c_int;
     pub fn myzkp_g2_msm(ctx: *mut myzkp_ctx, scalars_le: *const u8, points: *const u8, n: usize, out: *mut u8) -> c_int;
@@ -45,7 +53,7 @@ extern "C" {
     pub fn myzkp_kzg_commit_batch(ctx: *mut myzkp_ctx, coefs: *const *const u8, ns: *const usize, k: usize,
                                   out: *mut u8) -> c_int;
     pub fn myzkp_gemini_fold_commit(ctx: *mut myzkp_ctx, coefs_le: *const u8, n_pow2: usize, rhos_le: *const u8,
-                                    out: *mut u8, out_folds: *mut u8) -> c_int;
+                                    n_rhos: usize, out: *mut u8, out_folds: *mut u8) -> c_int;
     pub fn myzkp_kzg_batch_open(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, us_le: *const u8, k: usize,
                                 out_ys: *mut u8, out_w: *mut u8) -> c_int;
     pub fn myzkp_kzg_prove_degree_bound(ctx: *mut myzkp_ctx, coefs_le: *const u8, n: usize, d: usize,
@@ -72,6 +80,8 @@ extern "C" {
                                         d_out_c64: *mut c_void) -> c_int;
     pub fn myzkp_g1_exchange_sum_dev(ctx: *mut myzkp_ctx, d_partial_xyzz128: *const c_void, d_out_c64: *mut c_void) -> c_int;
     pub fn myzkp_kzg_commit_sharded(ctx: *mut myzkp_ctx, scalars_le: *const u8, n_local: usize, out_c: *mut u8) -> c_int;
+    pub fn myzkp_kzg_open_sharded(ctx: *mut myzkp_ctx, coefs_le: *const u8, n_local: usize, u_le: *const u8,
+                                  out_y: *mut u8, out_w: *mut u8) -> c_int;
     pub fn myzkp_kzg_open_sharded_dev(ctx: *mut myzkp_ctx, d_coefs: *const c_void, n_local: usize, u_le: *const u8,
                                       d_out_y32: *mut c_void, d_out_w64: *mut c_void) -> c_int;
     pub fn myzkp_g1_sum_partials_dev(ctx: *mut myzkp_ctx, d_partials: *const c_void, k: usize,
@@ -84,4 +94,17 @@ extern "C" {
     pub fn myzkp_test_field_op(ctx: *mut myzkp_ctx, field: c_int, op: c_int, a: *const u8, b: *const u8, out: *mut u8,
                                n: usize) -> c_int;
     pub fn myzkp_test_g1_op(ctx: *mut myzkp_ctx, op: c_int, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> c_int;
+
+    pub fn myzkp_device_count() -> c_int;
+    pub fn myzkp_mctx_create(out: *mut *mut myzkp_mctx, device_ids: *const c_int, n_dev: c_int) -> c_int;
+    pub fn myzkp_mctx_destroy(m: *mut myzkp_mctx) -> c_int;
+    pub fn myzkp_mctx_last_error(m: *const myzkp_mctx) -> *const c_char;
+    pub fn myzkp_mctx_world(m: *const myzkp_mctx) -> c_int;
+    pub fn myzkp_mctx_rank(m: *mut myzkp_mctx, g: c_int) -> *mut myzkp_ctx;
+    pub fn myzkp_mctx_srs_len(m: *const myzkp_mctx) -> usize;
+    pub fn myzkp_mctx_srs_generate_g1(m: *mut myzkp_mctx, alpha_le: *const u8, n: usize) -> c_int;
+    pub fn myzkp_mctx_srs_load_g1(m: *mut myzkp_mctx, affine_xy_le: *const u8, n: usize) -> c_int;
+    pub fn myzkp_mctx_kzg_commit(m: *mut myzkp_mctx, coefs_le: *const u8, n: usize, out_c: *mut u8) -> c_int;
+    pub fn myzkp_mctx_kzg_open(m: *mut myzkp_mctx, coefs_le: *const u8, n: usize, u_le: *const u8, out_y: *mut u8,
+                               out_w: *mut u8) -> c_int;
 }

@@ -8,6 +8,8 @@ use std::ptr;
 
 use myzkp::modules::algebra::curve::bn128::{Fq, Fq2, FqOrder, G1Point, G2Point, BN128};
 use myzkp::modules::algebra::field::Field;
+use myzkp::modules::algebra::gemini::SplitFoldError;
+use myzkp::modules::algebra::kzg::PublicKeyKZG;
 use myzkp::modules::algebra::polynomial::Polynomial;
 use myzkp::modules::algebra::ring::Ring;
 use myzkp_b200_sys as sys;
@@ -30,6 +32,41 @@ pub struct GpuPublicKeyKZG {
 impl Drop for GpuPublicKeyKZG {
     fn drop(&mut self) {
         unsafe { sys::myzkp_ctx_destroy(self.ctx) };
+    }
+}
+
+// A context may be used from any ONE thread at a time (every entry point selects its device first), so the handle
+// can move between threads - e.g. one thread per rank of the range-sharded prover.  It is not Sync.
+unsafe impl Send for GpuPublicKeyKZG {}
+
+/// The reference's public key (kzg.rs:8-11) moved to the GPU: powers_1 are uploaded once and become the resident
+/// SRS table (myzkp_srs_load_g1), powers_2 stay on the host for the verifier.  This is what lets existing callers
+/// that hold a `PublicKeyKZG` (das/avail.rs:38,96,132, das/eigenda.rs:44,99,119) switch to the device path.
+impl From<&PublicKeyKZG> for GpuPublicKeyKZG {
+    fn from(pk: &PublicKeyKZG) -> Self {
+        let mut ctx = ptr::null_mut();
+        let code = unsafe { sys::myzkp_ctx_create(&mut ctx, 0) };
+        assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
+        let mut bytes = Vec::with_capacity(64 * pk.powers_1.len());
+        for p in &pk.powers_1 {
+            bytes.extend_from_slice(&g1_to_bytes(p));
+        }
+        check(ctx, unsafe { sys::myzkp_srs_load_g1(ctx, bytes.as_ptr(), pk.powers_1.len()) });
+        GpuPublicKeyKZG { ctx, powers_2: pk.powers_2.clone() }
+    }
+}
+
+impl GpuPublicKeyKZG {
+    /// powers_1 read back from the device (kzg.rs:9)
+    pub fn powers_1(&self) -> Vec<G1Point> {
+        let n = unsafe { sys::myzkp_srs_len(self.ctx) };
+        let mut out = vec![0u8; 64 * n];
+        check(self.ctx, unsafe { sys::myzkp_srs_read_g1(self.ctx, 0, n, out.as_mut_ptr()) });
+        out.chunks_exact(64).map(|c| point_from_bytes(c.try_into().unwrap())).collect()
+    }
+    /// the same key in the reference's own type (e.g. to hand to the reference's verifier)
+    pub fn to_reference(&self) -> PublicKeyKZG {
+        PublicKeyKZG { powers_1: self.powers_1(), powers_2: self.powers_2.clone() }
     }
 }
 
@@ -109,14 +146,23 @@ fn g2_powers(ctx: *mut sys::myzkp_ctx, alpha: &FqOrder, g2: &G2Point, n: usize) 
 }
 
 fn setup(g1: &G1Point, g2: &G2Point, max_d: usize, n_g2: usize) -> GpuPublicKeyKZG {
-    assert!(*g1 == BN128::generator_g1());
     let alpha = FqOrder::random_element(&[]); // kzg.rs:28
+    setup_with_alpha(g1, g2, max_d, n_g2, &alpha)
+}
+
+/// setup with the trapdoor injected (tests, reproducible benches; the reference draws it unseeded, kzg.rs:28)
+pub fn setup_kzg_with_alpha(g1: &G1Point, g2: &G2Point, max_d: usize, alpha: &FqOrder) -> GpuPublicKeyKZG {
+    setup_with_alpha(g1, g2, max_d, 2, alpha)
+}
+
+fn setup_with_alpha(g1: &G1Point, g2: &G2Point, max_d: usize, n_g2: usize, alpha: &FqOrder) -> GpuPublicKeyKZG {
+    assert!(*g1 == BN128::generator_g1());
     let mut ctx = ptr::null_mut();
     let code = unsafe { sys::myzkp_ctx_create(&mut ctx, 0) };
     assert!(code == sys::MYZKP_OK, "no usable CUDA device (there is no CPU fallback)");
-    let a = scalar_to_le(&alpha);
+    let a = scalar_to_le(alpha);
     check(ctx, unsafe { sys::myzkp_srs_generate_g1(ctx, a.as_ptr(), 0, max_d + 1) });
-    let powers_2 = g2_powers(ctx, &alpha, g2, n_g2);
+    let powers_2 = g2_powers(ctx, alpha, g2, n_g2);
     GpuPublicKeyKZG { ctx, powers_2 }
 }
 
@@ -163,10 +209,14 @@ pub fn pairing_product_is_one(g1: &[G1Point], g2: &[G2Point], pk: &GpuPublicKeyK
     ok != 0
 }
 
-/// verify_kzg (kzg.rs:90-102): e(C, g2) == e(W, [alpha]g2 - [u]g2) * e(g1, g2)^y, evaluated as the product
-/// e(C, g2) * e(-W, [alpha - u]g2) * e([-y]g1, g2) == 1.  The three small group operations use the reference's
-/// own point arithmetic; the pairings run on the GPU.
-pub fn verify_kzg(u: &FqOrder, c: &CommitmentKZG, proof: &ProofKZG, g1: &G1Point, pk: &GpuPublicKeyKZG) -> bool {
+/// verify_kzg (kzg.rs:90-102), same argument list: e(C, g2) == e(W, [alpha]g2 - [u]g2) * e(g1, g2)^y, evaluated as
+/// the product e(C, g2) * e(-W, [alpha - u]g2) * e([-y]g1, g2) == 1.  g1 = powers_1[0] is read from the device
+/// (kzg.rs:91); the three small group operations use the reference's own point arithmetic; the pairings run on
+/// the GPU.
+pub fn verify_kzg(u: &FqOrder, c: &CommitmentKZG, proof: &ProofKZG, pk: &GpuPublicKeyKZG) -> bool {
+    let mut g1b = [0u8; 64];
+    check(pk.ctx, unsafe { sys::myzkp_srs_read_g1(pk.ctx, 0, 1, g1b.as_mut_ptr()) });
+    let g1 = &point_from_bytes(&g1b);
     let g2 = &pk.powers_2[0];
     let g2_alpha_minus_u = pk.powers_2[1].clone() - g2.mul_ref(u.clone().get_value());
     let minus_y = (FqOrder::zero() - proof.y.clone()).sanitize();
@@ -239,15 +289,27 @@ pub struct ProofGemini {
 
 /// split_and_fold (gemini.rs:51-103) fused with commit_gemini (gemini.rs:112-114): the folds are computed and committed
 /// on the GPU; returns the log2(n) + 1 commitments and the folded polynomials (without the original).
-pub fn split_and_fold_commit(coef: &[FqOrder], rhos: &[FqOrder], pk: &GpuPublicKeyKZG) -> (Vec<CommitmentKZG>, Vec<Polynomial<FqOrder>>) {
+pub fn split_and_fold_commit(
+    coef: &[FqOrder],
+    rhos: &[FqOrder],
+    pk: &GpuPublicKeyKZG,
+) -> Result<(Vec<CommitmentKZG>, Vec<Polynomial<FqOrder>>), SplitFoldError> {
     let n = coef.len();
     let m = rhos.len();
+    // the reference's own checks, before anything crosses the FFI (gemini.rs:55-66); the C ABI checks them again
+    // through its n_rhos argument, so a wrong count can never size a buffer
+    if n.count_ones() != 1 {
+        return Err(SplitFoldError::CoefsNotPowerOfTwo { found: n });
+    }
+    let log2_n = (usize::BITS - 1 - n.leading_zeros()) as usize;
+    if m != log2_n {
+        return Err(SplitFoldError::PointsLenMismatch { expected: log2_n, found: m });
+    }
     let (cb, rb) = (marshal_scalars(coef), marshal_scalars(rhos));
     let mut out = vec![0u8; 64 * (m + 1)];
     let mut folds = vec![0u8; 32 * n.saturating_sub(1)];
-    // non power-of-two n / wrong challenge count come back as an error (SplitFoldError, gemini.rs:55-66)
     check(pk.ctx, unsafe {
-        sys::myzkp_gemini_fold_commit(pk.ctx, cb.as_ptr(), n, rb.as_ptr(), out.as_mut_ptr(), folds.as_mut_ptr())
+        sys::myzkp_gemini_fold_commit(pk.ctx, cb.as_ptr(), n, rb.as_ptr(), m, out.as_mut_ptr(), folds.as_mut_ptr())
     });
     let cms = out.chunks_exact(64).map(|c| point_from_bytes(c.try_into().unwrap())).collect();
     let mut polys = Vec::with_capacity(m);
@@ -261,7 +323,7 @@ pub fn split_and_fold_commit(coef: &[FqOrder], rhos: &[FqOrder], pk: &GpuPublicK
         off += len;
         len /= 2;
     }
-    (cms, polys)
+    Ok((cms, polys))
 }
 
 /// open_gemini (gemini.rs:116-144)
@@ -320,4 +382,161 @@ pub fn commit_kzg_sharded(local_slice: &[FqOrder], pk: &GpuPublicKeyKZG) -> Comm
     let mut out = [0u8; 64];
     check(pk.ctx, unsafe { sys::myzkp_kzg_commit_sharded(pk.ctx, bytes.as_ptr(), local_slice.len(), out.as_mut_ptr()) });
     point_from_bytes(&out)
+}
+
+/// open_kzg of the whole polynomial from this rank's coefficient slice (every rank returns the same proof)
+pub fn open_kzg_sharded(local_slice: &[FqOrder], u: &FqOrder, pk: &GpuPublicKeyKZG) -> ProofKZG {
+    let bytes = marshal_scalars(local_slice);
+    let ub = scalar_to_le(u);
+    let (mut y, mut w) = ([0u8; 32], [0u8; 64]);
+    check(pk.ctx, unsafe {
+        sys::myzkp_kzg_open_sharded(pk.ctx, bytes.as_ptr(), local_slice.len(), ub.as_ptr(), y.as_mut_ptr(), w.as_mut_ptr())
+    });
+    ProofKZG { y: FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, &y)), w: point_from_bytes(&w) }
+}
+
+/// One process, several GPUs (csrc/multi.cu): the SRS is range-sharded over `devices`, commit / open split the
+/// coefficients, every GPU runs its range and the partials meet in the peer-memory exchange kernel.  One call from
+/// one host thread; the library drives the devices from its own threads.
+pub struct MultiGpuKZG {
+    m: *mut sys::myzkp_mctx,
+    pub powers_2: Vec<G2Point>,
+}
+unsafe impl Send for MultiGpuKZG {}
+
+impl Drop for MultiGpuKZG {
+    fn drop(&mut self) {
+        unsafe { sys::myzkp_mctx_destroy(self.m) };
+    }
+}
+
+fn mcheck(m: *mut sys::myzkp_mctx, code: i32) {
+    if code != sys::MYZKP_OK {
+        let msg = unsafe { CStr::from_ptr(sys::myzkp_mctx_last_error(m)) }.to_string_lossy().into_owned();
+        panic!("myzkp_b200 error {}: {}", code, msg);
+    }
+}
+
+impl MultiGpuKZG {
+    fn create(devices: &[i32]) -> *mut sys::myzkp_mctx {
+        let mut m = ptr::null_mut();
+        let code = unsafe { sys::myzkp_mctx_create(&mut m, devices.as_ptr(), devices.len() as i32) };
+        assert!(code == sys::MYZKP_OK, "no usable CUDA devices (there is no CPU fallback)");
+        m
+    }
+    /// setup_kzg (kzg.rs:27-40) over several GPUs, trapdoor injected
+    pub fn setup_with_alpha(devices: &[i32], g2: &G2Point, max_d: usize, alpha: &FqOrder) -> Self {
+        let m = Self::create(devices);
+        let a = scalar_to_le(alpha);
+        mcheck(m, unsafe { sys::myzkp_mctx_srs_generate_g1(m, a.as_ptr(), max_d + 1) });
+        let powers_2 = g2_powers(unsafe { sys::myzkp_mctx_rank(m, 0) }, alpha, g2, 2);
+        MultiGpuKZG { m, powers_2 }
+    }
+    /// an existing reference key, sharded over the devices
+    pub fn from_reference(devices: &[i32], pk: &PublicKeyKZG) -> Self {
+        let m = Self::create(devices);
+        let mut bytes = Vec::with_capacity(64 * pk.powers_1.len());
+        for p in &pk.powers_1 {
+            bytes.extend_from_slice(&g1_to_bytes(p));
+        }
+        mcheck(m, unsafe { sys::myzkp_mctx_srs_load_g1(m, bytes.as_ptr(), pk.powers_1.len()) });
+        MultiGpuKZG { m, powers_2: pk.powers_2.clone() }
+    }
+    /// commit_kzg (kzg.rs:57-59)
+    pub fn commit_kzg(&self, f: &Polynomial<FqOrder>) -> CommitmentKZG {
+        let bytes = marshal_scalars(&f.coef);
+        let mut out = [0u8; 64];
+        mcheck(self.m, unsafe { sys::myzkp_mctx_kzg_commit(self.m, bytes.as_ptr(), f.coef.len(), out.as_mut_ptr()) });
+        point_from_bytes(&out)
+    }
+    /// open_kzg (kzg.rs:61-72)
+    pub fn open_kzg(&self, f: &Polynomial<FqOrder>, u: &FqOrder) -> ProofKZG {
+        let bytes = marshal_scalars(&f.coef);
+        let ub = scalar_to_le(u);
+        let (mut y, mut w) = ([0u8; 32], [0u8; 64]);
+        mcheck(self.m, unsafe {
+            sys::myzkp_mctx_kzg_open(self.m, bytes.as_ptr(), f.coef.len(), ub.as_ptr(), y.as_mut_ptr(), w.as_mut_ptr())
+        });
+        ProofKZG { y: FqOrder::from_value(BigInt::from_bytes_le(Sign::Plus, &y)), w: point_from_bytes(&w) }
+    }
+}
+
+/// The reference's exact signatures (kzg.rs:27,57,61,90; gemini.rs:112) over the reference's own `PublicKeyKZG`:
+/// `use myzkp_b200::dropin::{setup_kzg, commit_kzg, open_kzg, verify_kzg}` instead of
+/// `use myzkp::modules::algebra::kzg::{...}` and nothing else changes at the call sites.  The device side of a key
+/// (context + resident table) is cached per key: the first call with a given `PublicKeyKZG` uploads powers_1
+/// (`From<&PublicKeyKZG>`), later calls find it by the key's address, length and end points.
+pub mod dropin {
+    use super::*;
+    use myzkp::modules::algebra::kzg::ProofKZG as RefProofKZG;
+    use std::sync::{Arc, Mutex, OnceLock};
+
+    #[derive(PartialEq, Clone)]
+    struct Fingerprint {
+        addr: usize,
+        len: usize,
+        first: [u8; 64],
+        last: [u8; 64],
+    }
+    fn fingerprint(pk: &PublicKeyKZG) -> Fingerprint {
+        let n = pk.powers_1.len();
+        Fingerprint {
+            addr: pk.powers_1.as_ptr() as usize,
+            len: n,
+            first: if n > 1 { g1_to_bytes(&pk.powers_1[1]) } else { [0u8; 64] },
+            last: if n > 0 { g1_to_bytes(&pk.powers_1[n - 1]) } else { [0u8; 64] },
+        }
+    }
+    struct Shared(Arc<Mutex<GpuPublicKeyKZG>>);
+    fn cache() -> &'static Mutex<Vec<(Fingerprint, Arc<Mutex<GpuPublicKeyKZG>>)>> {
+        static C: OnceLock<Mutex<Vec<(Fingerprint, Arc<Mutex<GpuPublicKeyKZG>>)>>> = OnceLock::new();
+        C.get_or_init(|| Mutex::new(Vec::new()))
+    }
+    fn device_key(pk: &PublicKeyKZG) -> Shared {
+        let fp = fingerprint(pk);
+        let mut c = cache().lock().unwrap();
+        if let Some((_, g)) = c.iter().find(|(f, _)| *f == fp) {
+            return Shared(g.clone());
+        }
+        let g = Arc::new(Mutex::new(GpuPublicKeyKZG::from(pk)));
+        if c.len() >= 4 {
+            c.remove(0); // a handful of keys at most stay resident
+        }
+        c.push((fp, g.clone()));
+        Shared(g)
+    }
+
+    /// kzg.rs:27-40: the powers are generated on the GPU and read back into the reference's struct; the device
+    /// side stays resident for the calls below.
+    pub fn setup_kzg(g1: &G1Point, g2: &G2Point, max_d: usize) -> PublicKeyKZG {
+        let gpu = super::setup_kzg(g1, g2, max_d);
+        let pk = gpu.to_reference();
+        cache().lock().unwrap().push((fingerprint(&pk), Arc::new(Mutex::new(gpu))));
+        pk
+    }
+    /// kzg.rs:57-59
+    pub fn commit_kzg(f: &Polynomial<FqOrder>, pk: &PublicKeyKZG) -> CommitmentKZG {
+        let k = device_key(pk);
+        let g = k.0.lock().unwrap();
+        super::commit_kzg(f, &g)
+    }
+    /// kzg.rs:61-72
+    pub fn open_kzg(f: &Polynomial<FqOrder>, u: &FqOrder, pk: &PublicKeyKZG) -> RefProofKZG {
+        let k = device_key(pk);
+        let g = k.0.lock().unwrap();
+        let p = super::open_kzg(f, u, &g);
+        RefProofKZG { y: p.y, w: p.w }
+    }
+    /// kzg.rs:90-102
+    pub fn verify_kzg(u: &FqOrder, c: &CommitmentKZG, proof: &RefProofKZG, pk: &PublicKeyKZG) -> bool {
+        let k = device_key(pk);
+        let g = k.0.lock().unwrap();
+        super::verify_kzg(u, c, &ProofKZG { y: proof.y.clone(), w: proof.w.clone() }, &g)
+    }
+    /// gemini.rs:112-114
+    pub fn commit_gemini(polys: &[Polynomial<FqOrder>], pk: &PublicKeyKZG) -> Vec<CommitmentKZG> {
+        let k = device_key(pk);
+        let g = k.0.lock().unwrap();
+        super::commit_gemini(polys, &g)
+    }
 }

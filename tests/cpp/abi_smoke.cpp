@@ -78,6 +78,13 @@ int main() {
       t1.join();
       if (!e0.empty() || !e1.empty()) { printf("FAIL sharded commit threw: [%s] [%s]\n", e0.c_str(), e1.c_str()); return 1; }
       if (c0.xy != c.xy || c1.xy != c.xy) { printf("FAIL sharded commit\n"); return 1; }
+      ProofKZG p0, p1;
+      std::thread t2([&] { try { p0 = open_kzg_sharded(lo, scalar_u64(5), r0); } catch (const std::exception& e) { e0 = e.what(); } });
+      std::thread t3([&] { try { p1 = open_kzg_sharded(hi, scalar_u64(5), r1); } catch (const std::exception& e) { e1 = e.what(); } });
+      t2.join();
+      t3.join();
+      if (!e0.empty() || !e1.empty()) { printf("FAIL sharded open threw: [%s] [%s]\n", e0.c_str(), e1.c_str()); return 1; }
+      if (p0.y != pr.y || p1.y != pr.y || !(p0.w == pr.w) || !(p1.w == pr.w)) { printf("FAIL sharded open\n"); return 1; }
     }
     printf("OK\n");
   } catch (const std::exception& e) {

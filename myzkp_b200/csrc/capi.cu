@@ -160,10 +160,10 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
     const uint32_t* sc = d_coefs + lo * 8;
     size_t len = hi - lo;
     if (u_le) {
-      MZ_TRY(fr_check_canonical(ctx, sc, len, flag));
       const bool top = (hi == n);
       if (!top) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(c0_prev, c0, 32, cudaMemcpyDeviceToDevice, ctx->stream));
-      MZ_TRY(fr_range_quotient(ctx, sc, len, u_le, nullptr, d_quot + lo * 8, c0, top ? nullptr : c0_prev));
+      // the scan checks canonicity of what it reads (no separate pass over the coefficients)
+      MZ_TRY(fr_range_quotient(ctx, sc, len, u_le, nullptr, d_quot + lo * 8, c0, top ? nullptr : c0_prev, flag));
       // q[i] = q_{lo+i} pairs with SRS point lo+i; the global top coefficient q_{n-1} is the zero carry
       sc = d_quot + lo * 8;
       if (top) len -= 1;
@@ -303,7 +303,7 @@ int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len) {
 }
 
 int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds) {
-  if (!ctx || rounds < -1 || rounds > 16) return MYZKP_ERR_INVALID_ARG;
+  if (!ctx || rounds < -2 || rounds > 16) return MYZKP_ERR_INVALID_ARG;
   ctx->baa_rounds = rounds;
   return MYZKP_OK;
 }
@@ -404,8 +404,7 @@ int myzkp_kzg_open_sharded_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n_loc
   uint32_t* carry = reinterpret_cast<uint32_t*>(s + kSmallY + 64);   // carry entering from above
   XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);               // partial, then c_0 right behind it
   uint32_t* c0 = reinterpret_cast<uint32_t*>(s + kSmallXyzz + sizeof(XYZZ));
-  if (n_local) MZ_TRY(fr_check_canonical(ctx, coefs, n_local, reinterpret_cast<int*>(s + kSmallFlag)));
-  MZ_TRY(fr_range_eval(ctx, coefs, n_local, u_le, pair, pair + 8));
+  MZ_TRY(fr_range_eval(ctx, coefs, n_local, u_le, pair, pair + 8, reinterpret_cast<int*>(s + kSmallFlag)));
   MZ_TRY(peer_exchange(ctx, 1, pair, 64, carry, nullptr));
   if (n_local) {
     MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n_local * 32));
@@ -463,9 +462,8 @@ int myzkp_kzg_open_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint
   }
   MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
   int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag);
-  MZ_TRY(fr_check_canonical(ctx, static_cast<const uint32_t*>(d_coefs), n, flag));
   MZ_TRY(fr_range_quotient(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, nullptr, ctx->scalars2.as<uint32_t>(),
-                           static_cast<uint32_t*>(d_out_y32)));
+                           static_cast<uint32_t*>(d_out_y32), nullptr, flag));
   // q has n-1 coefficients (q[n-1] is the zero carry entering from above)
   MZ_TRY(msm_xyzz(ctx, ctx->scalars2.as<uint32_t>(), n - 1, 0, res));
   return xyzz_to_bytes(ctx, res, 1, static_cast<uint8_t*>(d_out_w64));
@@ -477,7 +475,7 @@ int myzkp_fr_range_eval_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const
   if (!fr_bytes_canonical(u_le)) return fail(ctx, MYZKP_ERR_NONCANONICAL, "u >= r");
   MZ_TRY(begin_call(ctx));
   return fr_range_eval(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, static_cast<uint32_t*>(d_out_h32),
-                       static_cast<uint32_t*>(d_out_upow32));
+                       static_cast<uint32_t*>(d_out_upow32), reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag));
 }
 
 int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, const uint8_t u_le[32],
@@ -490,7 +488,8 @@ int myzkp_fr_range_quotient_dev(myzkp_ctx* ctx, const void* d_coefs, size_t n, c
     return MYZKP_OK;
   }
   return fr_range_quotient(ctx, static_cast<const uint32_t*>(d_coefs), n, u_le, carry_in_le,
-                           static_cast<uint32_t*>(d_q), static_cast<uint32_t*>(d_c0));
+                           static_cast<uint32_t*>(d_q), static_cast<uint32_t*>(d_c0), nullptr,
+                           reinterpret_cast<int*>(ctx->small.as<uint8_t>() + kSmallFlag));
 }
 
 // ---- host-buffer variants ------------------------------------------------
@@ -821,10 +820,9 @@ int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8
   if (n) {
     MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
     MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    MZ_TRY(fr_check_canonical(ctx, ctx->scalars.as<uint32_t>(), n, reinterpret_cast<int*>(s + kSmallFlag)));
   }
   MZ_TRY(fr_range_eval(ctx, ctx->scalars.as<uint32_t>(), n, u_le, reinterpret_cast<uint32_t*>(s + kSmallY),
-                       reinterpret_cast<uint32_t*>(s + kSmallY + 32)));
+                       reinterpret_cast<uint32_t*>(s + kSmallY + 32), reinterpret_cast<int*>(s + kSmallFlag)));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
   return end_call_check_flag(ctx);
 }
@@ -842,9 +840,8 @@ int myzkp_fr_quotient(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const u
   MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
   MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 32));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, coefs_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  MZ_TRY(fr_check_canonical(ctx, ctx->scalars.as<uint32_t>(), n, reinterpret_cast<int*>(s + kSmallFlag)));
   MZ_TRY(fr_range_quotient(ctx, ctx->scalars.as<uint32_t>(), n, u_le, nullptr, ctx->scalars2.as<uint32_t>(),
-                           reinterpret_cast<uint32_t*>(s + kSmallY)));
+                           reinterpret_cast<uint32_t*>(s + kSmallY), nullptr, reinterpret_cast<int*>(s + kSmallFlag)));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_y, s + kSmallY, 32, cudaMemcpyDeviceToHost, ctx->stream));
   if (n > 1) MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out_q, ctx->scalars2.p, (n - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
   return end_call_check_flag(ctx);

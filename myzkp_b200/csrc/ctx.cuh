@@ -89,6 +89,7 @@ struct myzkp_ctx {
   mz::DevBuf scalars;      // staged scalars / coefficients (n * 32 B)
   mz::DevBuf scalars2;     // quotient / folded coefficients
   mz::DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
+  mz::DevBuf sort_parts;   // partition plan of the MSD split (msm.cu, sort.cu)
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
   mz::DevBuf heads2;       // ping-pong levels of the head merge
@@ -135,7 +136,7 @@ namespace mz {
 template <class F>
 inline void for_each_scratch(myzkp_ctx* ctx, F f) {
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->sort_tmp, &ctx->sort_parts, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
                     &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
                     &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
   for (DevBuf* b : bufs) f(b);
@@ -208,7 +209,7 @@ int baa_accumulate(myzkp_ctx* ctx, const uint32_t* keys_s, const uint32_t* vals_
 // ---- sort.cu ----
 // LSD radix sort of (key, val) pairs by the low `bits` key bits; result in (*out_keys, *out_vals)
 int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
-                     int bits, uint32_t** out_keys, uint32_t** out_vals);
+                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts = nullptr, int P = 0);
 
 // ---- srs.cu ----
 int srs_alloc(myzkp_ctx* ctx, size_t n);
@@ -217,11 +218,12 @@ int srs_build_from_row0(myzkp_ctx* ctx);  // fills rows 1.. from row 0 (Montgome
 // ---- poly.cu ----
 // (h, u^n) of a coefficient range; both canonical 32 B written to device
 int fr_range_eval(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
-                  uint32_t* d_h, uint32_t* d_upow);
+                  uint32_t* d_h, uint32_t* d_upow, int* d_flag = nullptr);
 // with c_i = f_{lo+i} + u c_{i+1} and c_n = carry: d_q[i] = c_{i+1} (= q_{lo+i}), *d_c0 = c_0
-// (carry_le == NULL means 0)
+// (carry_le == NULL means 0); d_flag (optional, both): set to 1 when a coefficient is not canonical
 int fr_range_quotient(myzkp_ctx* ctx, const uint32_t* d_coefs, size_t n, const uint8_t u_le[32],
-                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0, const uint32_t* d_carry = nullptr);
+                      const uint8_t carry_le[32], uint32_t* d_q, uint32_t* d_c0, const uint32_t* d_carry = nullptr,
+                      int* d_flag = nullptr);
 int fr_fold(myzkp_ctx* ctx, const uint32_t* d_in, size_t n_out, const uint32_t* d_rho, uint32_t* d_out);
 int fr_check_canonical(myzkp_ctx* ctx, const uint32_t* d_in, size_t n, int* d_flag);
 

@@ -94,30 +94,58 @@ MZ_HD void xyzz_dbl(XYZZ& p) {
   p.zzz = fe_mul(w, p.zzz);
 }
 
+// Field-multiply policy of the hot formulas: InlineOps expands every multiply in place (the XYZZ-only
+// accumulate: its ~27 KB loop fits the 32 KB instruction cache); a kernel whose loop is larger passes a
+// policy whose multiplies are out-of-line calls, so the loop holds ONE copy of each multiply.
+struct InlineOps {
+  static MZ_HD Fq mul(const Fq& a, const Fq& b) { return MZ_MADD_MUL(a, b); }
+  static MZ_HD Fq sqr(const Fq& a) { return fe_sqr(a); }
+  static MZ_HD Fq mul2(const Fq& a, const Fq& b, const Fq& c, const Fq& d) { return MZ_MADD_MUL2(a, b, c, d); }
+};
+
+// 2 * (affine) with a multiply policy (see xyzz_mdbl)
+template <class OPS>
+MZ_HD XYZZ xyzz_mdbl_t(const Affine& p) {
+  XYZZ r;
+  Fq u = fe_dbl(p.y);
+  Fq v = OPS::sqr(u);
+  Fq w = OPS::mul(u, v);
+  Fq s = OPS::mul(p.x, v);
+  Fq xx = OPS::sqr(p.x);
+  Fq m = fe_add(fe_dbl(xx), xx);
+  r.x = fe_sub(OPS::sqr(m), fe_dbl(s));
+  r.y = OPS::mul2(m, fe_sub(s, r.x), fe_neg(w), p.y);
+  r.zz = v;
+  r.zzz = w;
+  return r;
+}
+
 // acc += q (mixed add, 8M + 2S) with the reference's case analysis
-MZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) {
+template <class OPS>
+MZ_HD void xyzz_madd_t(XYZZ& acc, const Affine& q) {
   if (affine_is_inf(q)) return;                      // P + inf       (curve.rs:135-137)
   if (xyzz_is_inf(acc)) {                            // inf + Q       (curve.rs:131-134)
     acc.x = q.x; acc.y = q.y; acc.zz = Fq::one(); acc.zzz = Fq::one();
     return;
   }
-  Fq p = fe_sub(MZ_MADD_MUL(q.x, acc.zz), acc.x);    // U2 - X1
-  Fq r = fe_sub(MZ_MADD_MUL(q.y, acc.zzz), acc.y);   // S2 - Y1
+  Fq p = fe_sub(OPS::mul(q.x, acc.zz), acc.x);       // U2 - X1
+  Fq r = fe_sub(OPS::mul(q.y, acc.zzz), acc.y);      // S2 - Y1
   if (p.is_zero()) {
-    if (r.is_zero()) acc = xyzz_mdbl(q);             // P + P         (curve.rs:139-141)
+    if (r.is_zero()) acc = xyzz_mdbl_t<OPS>(q);      // P + P         (curve.rs:139-141)
     else acc = xyzz_inf();                           // P + (-P)      (curve.rs:142-145)
     return;
   }
-  Fq pp = fe_sqr(p);
-  Fq ppp = MZ_MADD_MUL(p, pp);
-  Fq qq = MZ_MADD_MUL(acc.x, pp);
-  Fq x3 = fe_sub(fe_sub(fe_sqr(r), ppp), fe_dbl(qq));
-  Fq y3 = MZ_MADD_MUL2(r, fe_sub(qq, x3), fe_neg(acc.y), ppp);  // r (qq - x3) - y1 ppp, one reduction for both products
+  Fq pp = OPS::sqr(p);
+  Fq ppp = OPS::mul(p, pp);
+  Fq qq = OPS::mul(acc.x, pp);
+  Fq x3 = fe_sub(fe_sub(OPS::sqr(r), ppp), fe_dbl(qq));
+  Fq y3 = OPS::mul2(r, fe_sub(qq, x3), fe_neg(acc.y), ppp);  // r (qq - x3) - y1 ppp, one reduction for both products
   acc.x = x3;
   acc.y = y3;
-  acc.zz = MZ_MADD_MUL(acc.zz, pp);
-  acc.zzz = MZ_MADD_MUL(acc.zzz, ppp);
+  acc.zz = OPS::mul(acc.zz, pp);
+  acc.zzz = OPS::mul(acc.zzz, ppp);
 }
+MZ_HD void xyzz_madd(XYZZ& acc, const Affine& q) { xyzz_madd_t<InlineOps>(acc, q); }
 
 // acc += q (XYZZ + XYZZ, 12M + 2S) with the same case analysis
 MZ_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {

@@ -18,9 +18,12 @@
 //                      partial to the bucket's owner.
 //   5. msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
 //                      running sums, then a tree sum.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "ctx.cuh"
+#include "inv.cuh"
 
 namespace mz {
 
@@ -116,6 +119,170 @@ __global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const Recod
 }
 
 // ---------------------------------------------------------------------------
+// 1b. recode with an MSD split: entries leave the recode already partitioned by their high key bits
+// ---------------------------------------------------------------------------
+// A 22-bit bucket key costs three 8-bit radix passes over 1.6 GB of entries.  The recode kernel produces
+// the entries on chip anyway, so it can do the first (most significant) split for free: partition =
+// key >> low_bits (low_bits = 16: 33 partitions for c = 22, the last one holds the zero digits), and only
+// low_bits remain for the sort, which then runs inside each partition (sort.cu, locate_tile).
+//   msm_recode_count    per-partition entry counts (shared-memory counters, one global add per block and bin)
+//   msm_partition_plan  partition bases, tile bases, zeroed cursors (one block)
+//   msm_recode_scatter  recodes again, groups the block's entries by partition in shared memory, reserves
+//                       room in every partition with one atomic add each and copies the runs out
+// Order inside a partition is arbitrary (bucket sums commute); the sort passes that follow are stable.
+constexpr int kMaxParts = 260;
+constexpr int kPartCap = 6144;  // entries staged per block (48 KB of keys + values)
+// device layout of ctx->sort_parts (uint32): part_base[P+1] | tile_start[P+1] | counts[P] | cursor[P]
+constexpr int kSortTileEntries = 4096;  // = kSortTile of sort.cu
+
+struct RecodeCtl {
+  int c, W, low_bits, P;
+  uint32_t srs_n, srs_off, sentinel_key;
+};
+
+// digits of one scalar, least significant window first: f(w, key, val)
+template <class F>
+__device__ __forceinline__ void recode_scalar(const Fr& sc, const RecodeCtl& ctl, uint32_t key_base,
+                                              const uint8_t* __restrict__ row_of_bit, uint32_t i, F f) {
+  const int c = ctl.c;
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+  uint32_t carry = 0;
+  for (int w = 0; w < ctl.W; w++) {
+    const int bit = w * c;
+    const int limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      uint64_t two = sc.v[limb];
+      if (limb + 1 < 8) two |= (uint64_t)sc.v[limb + 1] << 32;
+      raw = (uint32_t)(two >> sh) & mask;
+    }
+    const uint32_t d = raw + carry;
+    const uint32_t neg = d > half ? 1u : 0u;
+    const uint32_t mag = neg ? ((1u << c) - d) : d;
+    carry = neg;
+    const uint32_t key = mag ? key_base + mag - 1 : ctl.sentinel_key;
+    const uint32_t idx = (uint32_t)row_of_bit[bit] * ctl.srs_n + ctl.srs_off + i;
+    f(w, key, idx | (neg << 31));
+  }
+}
+__device__ __forceinline__ Fr load_scalar(const uint32_t* scalars, size_t i) {
+  Fr sc;
+  const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  sc.v[0] = a.x; sc.v[1] = a.y; sc.v[2] = a.z; sc.v[3] = a.w;
+  sc.v[4] = b.x; sc.v[5] = b.y; sc.v[6] = b.z; sc.v[7] = b.w;
+  return sc;
+}
+
+// grid (blocks over the longest polynomial, K); every block handles `per_block` scalars
+__global__ void __launch_bounds__(256) msm_recode_count(RecodeDesc single, const RecodeDesc* __restrict__ descs,
+                                                        RecodeCtl ctl, uint32_t per_block,
+                                                        const uint8_t* __restrict__ row_of_bit,
+                                                        uint32_t* __restrict__ counts, int* __restrict__ flag) {
+  __shared__ uint32_t h[kMaxParts];
+  const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;
+  for (int p = threadIdx.x; p < ctl.P; p += blockDim.x) h[p] = 0;
+  __syncthreads();
+  const size_t lo = (size_t)blockIdx.x * per_block;
+  const size_t hi = lo + per_block < dsc.n ? lo + per_block : dsc.n;
+  bool bad = false;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const Fr sc = load_scalar(dsc.scalars, i);
+    bad |= !fe_is_canonical(sc);
+    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i,
+                  [&](int, uint32_t key, uint32_t) { atomicAdd(&h[key >> ctl.low_bits], 1u); });
+  }
+  if (bad) atomicOr(flag, 1);
+  __syncthreads();
+  for (int p = threadIdx.x; p < ctl.P; p += blockDim.x)
+    if (h[p]) atomicAdd(&counts[p], h[p]);
+}
+
+// one block: part_base / tile_start from the counts; cursors cleared
+__global__ void msm_partition_plan(uint32_t* __restrict__ parts, int P) {
+  uint32_t* part_base = parts;
+  uint32_t* tile_start = parts + (P + 1);
+  const uint32_t* counts = parts + 2 * (P + 1);
+  uint32_t* cursor = parts + 2 * (P + 1) + P;
+  if (threadIdx.x == 0) {
+    uint32_t b = 0, t = 0;
+    for (int p = 0; p < P; p++) {
+      part_base[p] = b;
+      tile_start[p] = t;
+      b += counts[p];
+      t += (counts[p] + kSortTileEntries - 1) / kSortTileEntries;
+    }
+    part_base[P] = b;
+    tile_start[P] = t;
+  }
+  for (int p = threadIdx.x; p < P; p += blockDim.x) cursor[p] = 0;
+}
+
+__global__ void __launch_bounds__(256) msm_recode_scatter(RecodeDesc single, const RecodeDesc* __restrict__ descs,
+                                                          RecodeCtl ctl, uint32_t per_block,
+                                                          const uint8_t* __restrict__ row_of_bit,
+                                                          uint32_t* __restrict__ parts, uint32_t* __restrict__ keys_out,
+                                                          uint32_t* __restrict__ vals_out) {
+  extern __shared__ uint32_t stage[];  // keys[kPartCap] | vals[kPartCap]
+  __shared__ uint32_t h[kMaxParts];      // counts, then running local cursors
+  __shared__ uint32_t loc_off[kMaxParts + 1];
+  __shared__ uint32_t gbase[kMaxParts];
+  uint32_t* s_keys = stage;
+  uint32_t* s_vals = stage + kPartCap;
+  const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;
+  const int P = ctl.P;
+  const uint32_t* part_base = parts;
+  uint32_t* cursor = parts + 2 * (P + 1) + P;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) h[p] = 0;
+  __syncthreads();
+  const size_t lo = (size_t)blockIdx.x * per_block;
+  const size_t hi = lo + per_block < dsc.n ? lo + per_block : dsc.n;
+  if (lo >= hi) return;
+  // sweep 1: counts
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const Fr sc = load_scalar(dsc.scalars, i);
+    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i,
+                  [&](int, uint32_t key, uint32_t) { atomicAdd(&h[key >> ctl.low_bits], 1u); });
+  }
+  __syncthreads();
+  // local offsets (P is small: one thread), global reservations
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int p = 0; p < P; p++) {
+      loc_off[p] = run;
+      run += h[p];
+    }
+    loc_off[P] = run;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const uint32_t cnt = h[p];
+    gbase[p] = cnt ? part_base[p] + atomicAdd(&cursor[p], cnt) : 0u;
+    h[p] = loc_off[p];  // becomes the running local cursor
+  }
+  __syncthreads();
+  // sweep 2: place
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const Fr sc = load_scalar(dsc.scalars, i);
+    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i, [&](int, uint32_t key, uint32_t val) {
+      const uint32_t pos = atomicAdd(&h[key >> ctl.low_bits], 1u);
+      s_keys[pos] = key;
+      s_vals[pos] = val;
+    });
+  }
+  __syncthreads();
+  const uint32_t total = loc_off[P];
+  for (uint32_t pos = threadIdx.x; pos < total; pos += blockDim.x) {
+    const uint32_t key = s_keys[pos];
+    const uint32_t p = key >> ctl.low_bits;
+    const uint32_t g = gbase[p] + (pos - loc_off[p]);
+    keys_out[g] = key;
+    vals_out[g] = s_vals[pos];
+  }
+}
+
+// ---------------------------------------------------------------------------
 // 3. segment accumulate
 // ---------------------------------------------------------------------------
 // Thread t owns sorted entries [t*L, (t+1)*L).  Its first run (bucket of its
@@ -167,6 +334,172 @@ __global__ void __launch_bounds__(kAccThreads, 4)
     v = v_next;
     pt = pt_next;
   }
+}
+
+// ---------------------------------------------------------------------------
+// 3b. segment accumulate with batched-affine pair sums (fused, one kernel)
+// ---------------------------------------------------------------------------
+// Same contract as msm_accumulate (segments of the sorted entry list, heads / buckets), but two
+// entries of the same bucket are first added in AFFINE coordinates and only the pair sum goes through
+// the XYZZ mixed addition:  per two entries  (5M + 1S) + (8M + 2S)  instead of  2 x (8M + 2S).
+// The affine addition needs 1 / (x_b - x_a); the thread shares ONE inversion among the kBaaBatch pairs
+// of a batch (Montgomery's trick, lane-private, so no synchronisation):
+//   phase 1  walk the batch backwards: suf[j] = prod_{i > j} dx_i (local memory), S = prod of all dx
+//   invert   I = 1 / S with the branch-free safegcd inverse (inv.cuh; integer-add pipe, no divergence)
+//   phase 2  walk forwards: 1 / dx_j = I * suf[j], I *= dx_j; lambda, x3, y3; xyzz_madd(acc, pair sum)
+// A pair that cannot be added in affine form - different buckets, an operand at infinity, equal x
+// (P + P or P - P), the sentinel - contributes dx = 1 to the product and its entries go through the
+// general mixed addition one by one, so every case of curve.rs:131-145 keeps its meaning.  In the
+// common split case (a ends a run, b starts the next) b simply becomes the new accumulator.
+// Points are gathered twice (x in phase 1, x and y in phase 2); prefetch.global.L2 a few pairs ahead
+// keeps both walks off the DRAM latency.
+// The loop is far larger than the 32 KB instruction cache when every multiply is expanded in place (ncu of
+// the first version: "no instruction" was the top stall, the multiply pipe 58 % busy), so this kernel's
+// multiplies are out-of-line calls - one copy each, arguments and result in registers.
+struct CallOps {
+  static __device__ __noinline__ Fq mul(Fq a, Fq b) { return fe_mul(a, b); }
+  static __device__ __noinline__ Fq sqr(Fq a) { return fe_sqr(a); }
+  static __device__ __noinline__ Fq mul2(Fq a, Fq b, Fq c, Fq d) { return fe_mul2(a, b, c, d); }
+};
+constexpr int kBaaBatch = 64;
+constexpr int kBaaPrefetch1 = 4;
+constexpr int kBaaAutoMinL = 1 << 30;  // automatic selection threshold on the segment length (off until measured)  // pairs ahead, phase 1 (1 multiply per pair)
+
+__device__ __forceinline__ Fq load_fq_ldg(const Fq* p) {
+  Fq r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kAccThreads, kMinBlocks)
+    msm_accumulate_baa(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M, uint32_t L,
+                       uint32_t sentinel, const Affine* __restrict__ tbl, XYZZ* __restrict__ buckets,
+                       XYZZ* __restrict__ heads, uint32_t* __restrict__ head_keys, uint64_t T) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint64_t s = t * L;  // L is even: pairs are 8-byte aligned in keys / vals
+  const uint64_t e = s + L < M ? s + L : M;
+  uint32_t cur = keys[s];
+  if (cur >= sentinel) {
+    head_keys[t] = sentinel;
+    return;
+  }
+  head_keys[t] = cur;
+  XYZZ acc = xyzz_inf();
+  bool first_run = true;
+  auto flush = [&]() {
+    if (first_run) store_xyzz(heads + t, acc);
+    else store_xyzz(buckets + cur, acc);
+    first_run = false;
+  };
+  auto load_pair = [&](uint64_t i0, uint32_t& ka, uint32_t& kb, uint32_t& va, uint32_t& vb) {
+    if (i0 + 1 < e) {
+      const uint2 k2 = *reinterpret_cast<const uint2*>(keys + i0);
+      const uint2 v2 = *reinterpret_cast<const uint2*>(vals + i0);
+      ka = k2.x; kb = k2.y; va = v2.x; vb = v2.y;
+    } else {
+      ka = keys[i0]; va = vals[i0];
+      kb = sentinel; vb = 0;
+    }
+  };
+  Fq suf[kBaaBatch];
+  const uint32_t npairs = (uint32_t)((e - s + 1) / 2);
+  for (uint32_t base = 0; base < npairs; base += kBaaBatch) {
+    const uint32_t cnt = npairs - base < (uint32_t)kBaaBatch ? npairs - base : (uint32_t)kBaaBatch;
+    const uint64_t b0 = s + 2 * (uint64_t)base;
+    // ---- phase 1: suffix products of the x differences ----
+    Fq S = Fq::one();
+#pragma unroll 1
+    for (int j = (int)cnt - 1; j >= 0; j--) {
+      if (j >= kBaaPrefetch1) {
+        uint32_t ka, kb, va, vb;
+        load_pair(b0 + 2 * (uint64_t)(j - kBaaPrefetch1), ka, kb, va, vb);
+        if (ka == kb && kb < sentinel) {
+          prefetch_l2(tbl + (va & 0x7fffffffu));
+          prefetch_l2(tbl + (vb & 0x7fffffffu));
+        }
+      }
+      uint32_t ka, kb, va, vb;
+      load_pair(b0 + 2 * (uint64_t)j, ka, kb, va, vb);
+      suf[j] = S;
+      Fq dx = Fq::one();
+      if (ka == kb && kb < sentinel) {
+        const Fq xa = load_fq_ldg(&tbl[va & 0x7fffffffu].x);
+        const Fq xb = load_fq_ldg(&tbl[vb & 0x7fffffffu].x);
+        const Fq d = fe_sub(xb, xa);
+        if (!xa.is_zero() && !xb.is_zero() && !d.is_zero()) dx = d;
+      }
+      S = CallOps::mul(S, dx);
+    }
+    // ---- one inversion for the batch ----
+    Fq I = fe_inv_safegcd(S);
+    // ---- phase 2: pair sums, then the mixed addition ----
+    {
+      uint32_t ka, kb, va, vb;
+      load_pair(b0, ka, kb, va, vb);
+      if (ka < sentinel) prefetch_l2(tbl + (va & 0x7fffffffu));
+      if (kb < sentinel) prefetch_l2(tbl + (vb & 0x7fffffffu));
+    }
+#pragma unroll 1
+    for (uint32_t j = 0; j < cnt; j++) {
+      uint32_t ka, kb, va, vb;
+      load_pair(b0 + 2 * (uint64_t)j, ka, kb, va, vb);
+      if (ka >= sentinel) break;  // nothing but sentinels from here on
+      if (j + 1 < cnt) {
+        uint32_t ka2, kb2, va2, vb2;
+        load_pair(b0 + 2 * (uint64_t)(j + 1), ka2, kb2, va2, vb2);
+        if (ka2 < sentinel) prefetch_l2(tbl + (va2 & 0x7fffffffu));
+        if (kb2 < sentinel) prefetch_l2(tbl + (vb2 & 0x7fffffffu));
+      }
+      const bool has_b = kb < sentinel;
+      Affine a = load_affine(tbl + (va & 0x7fffffffu));
+      Affine b;
+      b.x = Fq::zero(); b.y = Fq::zero();
+      if (has_b) b = load_affine(tbl + (vb & 0x7fffffffu));
+      bool valid = false;
+      Fq dx = Fq::one();
+      if (ka == kb && has_b) {
+        const Fq d = fe_sub(b.x, a.x);
+        if (!a.x.is_zero() && !b.x.is_zero() && !d.is_zero()) {
+          dx = d;
+          valid = true;
+        }
+      }
+      if (va >> 31) a.y = fe_neg(a.y);
+      if (vb >> 31) b.y = fe_neg(b.y);
+      const Fq inv = CallOps::mul(I, suf[j]);
+      I = CallOps::mul(I, dx);
+      Affine op = a;
+      if (valid) {
+        const Fq lam = CallOps::mul(fe_sub(b.y, a.y), inv);
+        const Fq x3 = fe_sub(fe_sub(CallOps::sqr(lam), a.x), b.x);
+        op.y = fe_sub(CallOps::mul(lam, fe_sub(a.x, x3)), a.y);
+        op.x = x3;
+      }
+      if (ka != cur) {
+        flush();
+        cur = ka;
+        acc = xyzz_inf();
+      }
+      xyzz_madd_t<CallOps>(acc, op);
+      if (!valid) {
+        if (!has_b) break;  // b is the sentinel or past the end of the segment
+        if (kb != ka) {     // a closed its run, b opens the next one
+          flush();
+          cur = kb;
+          acc = xyzz_from_affine(b);
+        } else {
+          xyzz_madd_t<CallOps>(acc, b);  // same bucket, not addable in affine form (equal x, infinity): general path
+        }
+      }
+    }
+  }
+  flush();
 }
 
 // 4. head merge.  Heads with the same key form a chain (consecutive, since segments are
@@ -444,16 +777,51 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
     MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->descs.p, descs.data(), K * sizeof(RecodeDesc), cudaMemcpyHostToDevice, ctx->stream));
     d_descs = ctx->descs.as<RecodeDesc>();
   }
-  if (n) {
+  // MSD split inside the recode when the key has more than 16 bits: the sort then only handles the low 16
+  // (or 24) bits, inside each partition
+  int low_bits = 0, P = 0;
+  if (sort_bits > 16 && !getenv("MZ_NO_PARTITION")) {
+    low_bits = 16;
+    if (((uint64_t)nb >> low_bits) + 1 > (uint64_t)(kMaxParts - 3)) low_bits = 24;
+    if (sort_bits > low_bits) P = (int)(((uint64_t)nb >> low_bits) + 1);
+    if (P < 2 || P > kMaxParts - 3) { P = 0; low_bits = 0; }
+  }
+  const uint32_t* d_parts = nullptr;
+  if (n && P) {
+    RecodeCtl ctl{c, W, low_bits, P, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb};
+    MZ_CUDA_TRY(ctx, ctx->sort_parts.ensure((size_t)(4 * P + 8) * sizeof(uint32_t)));
+    uint32_t* parts = ctx->sort_parts.as<uint32_t>();
+    uint32_t* counts = parts + 2 * (P + 1);
+    MZ_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)P * sizeof(uint32_t), ctx->stream));
+    uint32_t per_block = (uint32_t)(kPartCap / W);
+    if (per_block < 1) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window too small for the partitioned recode");
+    const unsigned gx = (unsigned)((n + per_block - 1) / per_block);
+    msm_recode_count<<<dim3(gx, (unsigned)K), 256, 0, ctx->stream>>>(descs[0], d_descs, ctl, per_block, ctx->d_row_of_bit,
+                                                                      counts, flag);
+    MZ_LAUNCH_CHECK(ctx);
+    msm_partition_plan<<<1, 256, 0, ctx->stream>>>(parts, P);
+    MZ_LAUNCH_CHECK(ctx);
+    static bool attr_set[64] = {};
+    if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
+      MZ_CUDA_TRY(ctx, cudaFuncSetAttribute(msm_recode_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            2 * kPartCap * (int)sizeof(uint32_t)));
+      attr_set[ctx->device] = true;
+    }
+    msm_recode_scatter<<<dim3(gx, (unsigned)K), 256, 2 * kPartCap * sizeof(uint32_t), ctx->stream>>>(
+        descs[0], d_descs, ctl, per_block, ctx->d_row_of_bit, parts, keys_a, vals_a);
+    MZ_LAUNCH_CHECK(ctx);
+    d_parts = parts;
+  } else if (n) {
     msm_recode<<<dim3((unsigned)((n + 255) / 256), (unsigned)K), 256, 0, ctx->stream>>>(
         descs[0], d_descs, c, W, ctx->d_row_of_bit, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb, keys_a, vals_a, flag);
     MZ_LAUNCH_CHECK(ctx);
   }
 
   MZ_PHASE(1);
-  // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit)
+  // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit; only the low bits when partitioned)
   uint32_t *keys_s = nullptr, *vals_s = nullptr;
-  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, sort_bits, &keys_s, &vals_s));
+  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, d_parts ? low_bits : sort_bits, &keys_s, &vals_s,
+                          d_parts, P));
 
   // 3. accumulate
   // Segment length: enough segments to fill the GPU several times over, but not much
@@ -477,6 +845,7 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
       if (l2 >= 8 && l2 <= 256) L = (uint32_t)l2;
     }
   }
+  L += L & 1;  // even: the fused batched-affine accumulate reads (key, val) pairs as aligned 8-byte words
   if (M == 0) {  // nothing but empty polynomials: every bucket is the point at infinity
     MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
     ctx->phase_pending = false;
@@ -487,10 +856,21 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
   MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(2);
-  // batched-affine rounds pay off when runs are long enough to pair up (avg run >= 4)
+  // Accumulate variants (myzkp_ctx_set_baa_rounds): 0 = XYZZ mixed additions only; -2 = fused batched-affine
+  // pair sums (msm_accumulate_baa); -1 = automatic: fused when segments are long enough for the lane-private
+  // batch inversion to amortise; 1..3 = the older multi-pass rounds (baa.cu, kept for comparison).
   int baa = ctx->baa_rounds;
-  if (baa < 0) baa = 0;  // automatic: off until measured faster on the target
-  if (baa > 0 && L >= 4) {
+  const bool fused = (baa == -2 && L >= 4) || (baa == -1 && L >= (uint32_t)kBaaAutoMinL);
+  if (fused) {
+    static const int minb = getenv("MZ_BAA_MINB") ? atoi(getenv("MZ_BAA_MINB")) : 4;  // experiment knob
+    if (minb == 3)
+      msm_accumulate_baa<3><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+    else
+      msm_accumulate_baa<4><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+    MZ_LAUNCH_CHECK(ctx);
+  } else if (baa > 0 && L >= 4) {
     MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, buckets, ctx->heads.as<XYZZ>(),
                           ctx->head_keys.as<uint32_t>(), T));
   } else {

@@ -122,16 +122,64 @@ __device__ __forceinline__ uint32_t warp_match_digit(uint32_t d, bool valid) {
   return peers;
 }
 
+// Partitioned sort: the entry list is a sequence of P partitions (MSD split done by the recode kernel,
+// msm.cu) that are sorted independently by their low key bits.  parts = [part_base[P + 1] | tile_start[P + 1]]
+// on the device: partition p owns entries [part_base[p], part_base[p + 1]) and tiles
+// [tile_start[p], tile_start[p + 1]).  Its histogram block is laid out [digit][tile of p] right behind the
+// blocks of the partitions before it, so ONE exclusive scan over everything yields, for every (partition,
+// digit, tile), the global position of that run: everything in front of a partition sums to part_base[p].
+// parts == nullptr: a single partition [0, n) with ntiles tiles (plain LSD radix sort).
+struct TileRef {
+  uint64_t base;       // first entry of the tile
+  uint32_t count;      // entries in the tile (0: the tile does not exist)
+  size_t hist_base;    // index of (digit 0, this tile) in the histogram array
+  uint32_t hist_stride;  // distance between consecutive digits
+};
+__device__ __forceinline__ TileRef locate_tile(uint32_t tile, const uint32_t* __restrict__ parts, int P, uint64_t n,
+                                               uint32_t ntiles) {
+  TileRef r;
+  if (!parts) {
+    r.base = (uint64_t)tile * kSortTile;
+    r.count = tile < ntiles ? (uint32_t)((n - r.base) < (uint64_t)kSortTile ? (n - r.base) : kSortTile) : 0u;
+    r.hist_base = tile;
+    r.hist_stride = ntiles;
+    return r;
+  }
+  const uint32_t* part_base = parts;
+  const uint32_t* tile_start = parts + (P + 1);
+  if (tile >= tile_start[P]) {
+    r.base = 0; r.count = 0; r.hist_base = 0; r.hist_stride = 0;
+    return r;
+  }
+  int lo = 0, hi = P;  // tile_start[lo] <= tile < tile_start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tile_start[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const uint32_t t0 = tile_start[lo], tl = tile - t0;
+  r.base = (uint64_t)part_base[lo] + (uint64_t)tl * kSortTile;
+  const uint64_t left = (uint64_t)part_base[lo + 1] - r.base;
+  r.count = (uint32_t)(left < (uint64_t)kSortTile ? left : kSortTile);
+  r.hist_stride = tile_start[lo + 1] - t0;
+  r.hist_base = (size_t)kRadix * t0 + tl;
+  return r;
+}
+
 __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* __restrict__ keys, uint64_t n, int shift,
-                                                               uint32_t* __restrict__ hist, uint32_t ntiles) {
+                                                               uint32_t* __restrict__ hist, uint32_t ntiles,
+                                                               const uint32_t* __restrict__ parts, int P) {
   __shared__ uint32_t h[kRadix];
+  __shared__ TileRef s_ref;
   h[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_ref = locate_tile(blockIdx.x, parts, P, n, ntiles);
   __syncthreads();
-  const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
-  // all loads first (16-byte vectors, order inside the tile is irrelevant for counting),
-  // then the shared-memory atomics: keeps 4 independent loads per thread in flight
+  const TileRef ref = s_ref;
+  if (ref.count == 0) return;
+  const uint64_t base = ref.base;
+  // all loads first (16-byte vectors when the tile is whole and aligned; order inside the tile is
+  // irrelevant for counting), then the shared-memory atomics
   uint32_t k[kSortItems];
-  if (base + kSortTile <= n) {
+  if (ref.count == kSortTile && (base & 3) == 0) {
     const uint4* src = reinterpret_cast<const uint4*>(keys + base);
 #pragma unroll
     for (int i = 0; i < kSortItems / 4; i++) {
@@ -143,12 +191,12 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
   } else {
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
-      uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-      if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1u);
+      uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
+      if (p < ref.count) atomicAdd(&h[(keys[base + p] >> shift) & (kRadix - 1)], 1u);
     }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+  hist[ref.hist_base + (size_t)threadIdx.x * ref.hist_stride] = h[threadIdx.x];
 }
 
 // Persistent: each block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile's keys,
@@ -156,8 +204,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
 // DRAM latency is covered by the ranking work rather than by occupancy.
 __global__ void __launch_bounds__(kSortThreads, 2)
     sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
-                      const uint32_t* __restrict__ hist_scanned, uint32_t ntiles, uint32_t* __restrict__ keys_out,
-                      uint32_t* __restrict__ vals_out) {
+                      const uint32_t* __restrict__ hist_scanned, uint32_t ntiles_arg, uint32_t* __restrict__ keys_out,
+                      uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ parts, int P) {
   __shared__ uint32_t s_keys[kSortTile];
   __shared__ uint32_t s_vals[kSortTile];
   __shared__ uint32_t cnt[kSortWarps][kRadix];  // per-warp digit counters, then per-warp bases
@@ -168,11 +216,14 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   // warp-blocked arrangement: warp w owns tile entries [w*512, (w+1)*512) in index order
   const uint32_t wbase = (uint32_t)w * (32 * kSortItems);
 
+  const uint32_t ntiles = parts ? parts[2 * P + 1] : ntiles_arg;  // tile_start[P]
   uint32_t k[kSortItems], v[kSortItems], kn[kSortItems], vn[kSortItems], rank[kSortItems];
-  uint32_t gb = 0, gbn = 0;
+  uint32_t gb = 0, gbn = 0, tn_next = 0;
   auto fetch = [&](uint32_t tile, uint32_t* kk, uint32_t* vv, uint32_t& g) {
-    const uint64_t tb = (uint64_t)tile * kSortTile;
-    const uint32_t tn = (uint32_t)((n - tb) < (uint64_t)kSortTile ? (n - tb) : kSortTile);
+    const TileRef ref = locate_tile(tile, parts, P, n, ntiles);
+    const uint64_t tb = ref.base;
+    const uint32_t tn = ref.count;
+    tn_next = tn;
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
       uint32_t p = wbase + i * 32 + lane;
@@ -183,13 +234,12 @@ __global__ void __launch_bounds__(kSortThreads, 2)
       uint32_t p = wbase + i * 32 + lane;
       vv[i] = p < tn ? vals_in[tb + p] : 0u;
     }
-    g = hist_scanned[(size_t)threadIdx.x * ntiles + tile];
+    g = hist_scanned[ref.hist_base + (size_t)threadIdx.x * ref.hist_stride];
   };
   uint32_t tile = blockIdx.x;
   if (tile < ntiles) fetch(tile, kn, vn, gbn);
   for (; tile < ntiles; tile += gridDim.x) {
-    const uint64_t tile_base = (uint64_t)tile * kSortTile;
-    const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)kSortTile ? (n - tile_base) : kSortTile);
+    const uint32_t tile_n = tn_next;
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) { k[i] = kn[i]; v[i] = vn[i]; }
     gb = gbn;
@@ -273,13 +323,16 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 // ---------------------------------------------------------------------------
 // Sorts n (key, val) pairs by the low `bits` key bits.  The result lands in
 // (*out_keys, *out_vals), which alias either the a- or the b-buffers.
+// d_parts / P (optional): the list is already split into P partitions by its high key bits (layout in the
+// comment above locate_tile); each partition is then sorted on its own by the low `bits` bits.
 int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
-                     int bits, uint32_t** out_keys, uint32_t** out_vals) {
+                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts, int P) {
   *out_keys = keys_a;
   *out_vals = vals_a;
   if (n == 0 || bits <= 0) return MYZKP_OK;
   if (n >= (1ull << 32)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "too many entries to sort");
-  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  // with partitions every partition may end in a partial tile: an upper bound on the tile count
+  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile) + (d_parts ? (uint32_t)P : 0u);
   const size_t hist_len = (size_t)ntiles * kRadix;
   const size_t nchunks = (hist_len + kScanChunk - 1) / kScanChunk;
   MZ_CUDA_TRY(ctx, ctx->sort_tmp.ensure((hist_len + nchunks + 64) * sizeof(uint32_t)));
@@ -287,7 +340,9 @@ int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_
   uint32_t* sums = hist + hist_len;
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int shift = 0; shift < bits; shift += 8) {
-    sort_tile_hist<<<ntiles, kSortThreads, 0, ctx->stream>>>(ki, n, shift, hist, ntiles);
+    // tiles past the last real one (partition mode) leave their slots untouched: those lie behind every
+    // used slot in scan order, so whatever they hold cannot reach a used prefix
+    sort_tile_hist<<<ntiles, kSortThreads, 0, ctx->stream>>>(ki, n, shift, hist, ntiles, d_parts, P);
     MZ_LAUNCH_CHECK(ctx);
     scan_chunk_sums<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
     MZ_LAUNCH_CHECK(ctx);
@@ -296,7 +351,7 @@ int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_
     scan_apply<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
     MZ_LAUNCH_CHECK(ctx);
     const uint32_t sblocks = ntiles < (uint32_t)ctx->sm_count * 2 ? ntiles : (uint32_t)ctx->sm_count * 2;
-    sort_tile_scatter<<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo);
+    sort_tile_scatter<<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
     MZ_LAUNCH_CHECK(ctx);
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;

@@ -19,7 +19,7 @@ RR = 1 << 256
 def _build(name):
     src = os.path.join(HERE, "emul", f"{name}.cpp")
     out = os.path.join(HERE, "emul", f"lib{name}.so")
-    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh", "g2.cuh", "pairing.cuh")]
+    hdrs = [os.path.join(HERE, "..", "myzkp_b200", "csrc", h) for h in ("field.cuh", "g1.cuh", "g2.cuh", "pairing.cuh", "inv.cuh", "baa.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)
@@ -88,8 +88,14 @@ def test_field_ops(name, m):
         exp = (pow(x, -1, m) if x else 0) * RR % m
         assert u1("inv", x * RR % m) == exp
         assert u1("inv_bingcd", x * RR % m) == exp
+        assert u1("inv_safegcd", x * RR % m) == exp
     for x in [1, 2, m - 1, m - 2, (m + 1) // 2, 3, 1 << 200] + [rnd.randrange(1, m) for _ in range(300)]:
         assert u1("inv_bingcd", x * RR % m) == pow(x, -1, m) * RR % m
+    # the branch-free safegcd inverse (csrc/inv.cuh): the Montgomery representative can be ANY residue, so
+    # feed raw residues of every shape (small, near the modulus, single bits, sparse) and many random ones
+    shapes = [1, 2, 3, m - 1, m - 2, (m + 1) // 2, (m - 1) // 2] + [1 << k for k in range(0, 254, 7)] + [m - (1 << k) for k in range(1, 250, 11)]
+    for x in shapes + [rnd.randrange(1, m) for _ in range(3000)]:
+        assert u1("inv_safegcd", x) == pow(x * pow(RR, -1, m) % m, -1, m) * RR % m
 
 
 

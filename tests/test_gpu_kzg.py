@@ -474,8 +474,8 @@ def test_batched_affine_rounds_on_device(ctx):
     try:
         for name, sc in dists.items():
             exp = o.expected_commit(sc, alpha)
-            for rounds in (1, 2, 3, 6):
-                for c, seg in ((8, 0), (12, 5), (16, 0), (16, 64), (20, 0)):
+            for rounds in (-2, 1, 2, 3, 6):  # -2 = the fused pair-sum accumulate (msm_accumulate_baa)
+                for c, seg in ((8, 0), (12, 5), (16, 0), (16, 64), (20, 0)) + (((8, 300), (12, 130), (4, 1000), (8, 7)) if rounds == -2 else ()):
                     ctx.set_baa_rounds(rounds)
                     ctx.set_msm_params(c, seg)
                     assert ctx.commit(sc) == exp, (name, rounds, c, seg)
@@ -488,9 +488,9 @@ def test_batched_affine_rounds_on_device(ctx):
         exp = None
         for p_ in pts:
             exp = o._fast_add(exp, p_)
-        for rounds in (1, 2, 4):
+        for rounds in (-2, 1, 2, 4):
             ctx.set_baa_rounds(rounds)
-            for c, seg in ((8, 0), (8, 4), (16, 3)):
+            for c, seg in ((8, 0), (8, 4), (16, 3), (8, 64), (4, 10)):
                 ctx.set_msm_params(c, seg)
                 assert ctx.commit(sc) == exp, (rounds, c, seg)
     finally:
@@ -833,3 +833,55 @@ def test_open_and_commit_at_2pow24(ctx):
         ctx.sync()  # reported once, then cleared
     finally:
         ctx.srs_generate(alpha, 16)  # release the 70 GiB table for the tests that follow
+
+
+def test_quotient_scan_ragged_sizes_carries_and_special_points(ctx):
+    """The single-pass look-back scan (csrc/poly.cu) against the oracle's synthetic division
+    (polynomial.rs:371-405 for a linear divisor): sizes around the tile (2048) and warp-chunk (16, 512)
+    boundaries, u in {0, 1, r-1, random}, a non-zero carry entering the range (sharded open), and the
+    evaluation-only form; also a non-canonical coefficient must raise the flag through the fused check."""
+    import torch
+
+    rng = random.Random(77)
+    sizes = [1, 2, 15, 16, 17, 511, 512, 513, 2047, 2048, 2049, 4095, 4096, 4097, 6144, 70001, (1 << 17) + 5]
+    for n in sizes:
+        ints = [rng.randrange(R) for _ in range(n)]
+        coefs = synth.ints_to_limbs(ints)
+        us = [rng.randrange(R)] if n > 5000 else [0, 1, R - 1, rng.randrange(R)]
+        for u in us:
+            ey, eq = o.synthetic_division(ints, u)
+            yq, q = ctx.fr_quotient(coefs, u)
+            assert yq == ey, (n, u)
+            assert synth.limbs_to_ints(q.view(np.uint64).reshape(-1, 4)) == eq, (n, u)
+            assert ctx.fr_eval(coefs, u) == ey, (n, u)
+        # carry entering the range from above + (h, u^n) of the range, device-pointer forms
+        u = rng.randrange(R)
+        carry = rng.randrange(R)
+        d = torch.from_numpy(coefs.view(np.int64).reshape(-1).copy()).cuda()
+        dq = torch.zeros(n * 4, dtype=torch.int64, device="cuda")
+        dc0 = torch.zeros(12, dtype=torch.int64, device="cuda")
+        ctx.fr_range_quotient_dev(d.data_ptr(), n, u, carry, dq.data_ptr(), dc0.data_ptr())
+        ctx.fr_range_eval_dev(d.data_ptr(), n, u, dc0.data_ptr() + 32, dc0.data_ptr() + 64)
+        ctx.sync()
+        c = carry
+        exp_q = [0] * n
+        for i in range(n - 1, -1, -1):
+            exp_q[i] = c
+            c = (ints[i] + u * c) % R
+        got_q = synth.limbs_to_ints(dq.cpu().numpy().view(np.uint64).reshape(-1, 4))
+        assert got_q == exp_q, n
+        got = synth.limbs_to_ints(dc0.cpu().numpy().view(np.uint64).reshape(-1, 4))
+        assert got[0] == c, n
+        h = 0
+        for i in range(n - 1, -1, -1):
+            h = (ints[i] + u * h) % R
+        assert got[1] == h and got[2] == pow(u, n, R), n
+    # fused canonicity check
+    n = 5000
+    ints = [rng.randrange(R) for _ in range(n)]
+    coefs = synth.ints_to_limbs(ints)
+    coefs[3333] = synth.ints_to_limbs([R])[0]  # r itself: the smallest non-canonical value
+    with pytest.raises(mz.MyzkpError):
+        ctx.fr_quotient(coefs, 5)
+    with pytest.raises(mz.MyzkpError):
+        ctx.fr_eval(coefs, 5)

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmyzkp_b200.so")
+# MYZKP_B200_LIB: development knob to load an experimental build of the same library (still CUDA-only)
+LIB_PATH = os.environ.get("MYZKP_B200_LIB") or os.path.join(_HERE, "libmyzkp_b200.so")
 
 MYZKP_OK = 0
 ERR_NAMES = {-1: "INVALID_ARG", -2: "NONCANONICAL", -3: "CUDA", -4: "OOM", -5: "NO_SRS"}

@@ -781,35 +781,29 @@ int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* point
     memset(out, 0, 64);
     return MYZKP_OK;
   }
-  // caller-supplied points (accumulate_curve_points-style call sites, zksnark/utils.rs:83-93): the resident
-  // table is set aside, a temporary table is built for these points, and the same pipeline runs
-  Affine* saved_table = ctx->table;
-  const size_t saved_n = ctx->srs_n;
-  const int saved_rows = ctx->table_rows;
-  const uint32_t saved_windows = ctx->windows;
-  int saved_row_bits[mz::kMaxTableRows];
-  uint8_t saved_row_of_bit[256];
-  memcpy(saved_row_bits, ctx->row_bits, sizeof saved_row_bits);
-  memcpy(saved_row_of_bit, ctx->row_of_bit, sizeof saved_row_of_bit);
-  ctx->table = nullptr;
-  ctx->srs_n = 0;
-  int rc = myzkp_srs_load_g1(ctx, points_or_null, n);
-  if (rc == MYZKP_OK) rc = myzkp_kzg_commit(ctx, scalars_le, n, out);
-  std::string err = ctx->err;
-  if (ctx->table) cudaFree(ctx->table);
-  ctx->table = saved_table;
-  ctx->srs_n = saved_n;
-  ctx->table_rows = saved_rows;
-  ctx->windows = saved_windows;
-  memcpy(ctx->row_bits, saved_row_bits, sizeof saved_row_bits);
-  memcpy(ctx->row_of_bit, saved_row_of_bit, sizeof saved_row_of_bit);
-  if (ctx->d_row_of_bit) {
-    cudaMemcpyAsync(ctx->d_row_of_bit, ctx->row_of_bit, 256, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(ctx->d_row_bits, ctx->row_bits, sizeof(int) * mz::kMaxTableRows, cudaMemcpyHostToDevice, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-  }
-  ctx->err = err;
-  return rc;
+  // caller-supplied points (accumulate_curve_points-style call sites, zksnark/utils.rs:83-93): classic windowed
+  // Pippenger over the points as given (msm_points_xyzz) - no table of multiples is built, the resident SRS
+  // is not touched, and the call costs about one MSM plus a fixed ~1 ms window combine
+  MZ_TRY(begin_call(ctx));  // (scalars >= r are caught by the recode kernel's canonicity flag)
+  uint8_t* s = ctx->small.as<uint8_t>();
+  MZ_CUDA_TRY(ctx, ctx->scalars.ensure(n * 32));
+  MZ_CUDA_TRY(ctx, ctx->scalars2.ensure(n * 64));
+  MZ_CUDA_TRY(ctx, ctx->caller_points.ensure(n * sizeof(Affine)));
+  int* pflag = reinterpret_cast<int*>(s + 528);  // own word: 512 is the sticky scalar flag
+  MZ_CUDA_TRY(ctx, cudaMemsetAsync(pflag, 0, sizeof(int), ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_le, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars2.p, points_or_null, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_TRY(points_import(ctx, ctx->scalars2.as<uint32_t>(), n, ctx->caller_points.as<Affine>(), pflag));
+  XYZZ* res = reinterpret_cast<XYZZ*>(s + kSmallXyzz);
+  uint8_t* d_pt = s + kSmallPoint;
+  MZ_TRY(msm_points_xyzz(ctx, ctx->scalars.as<uint32_t>(), ctx->caller_points.as<Affine>(), n, res));
+  MZ_TRY(xyzz_to_bytes(ctx, res, 1, d_pt));
+  int h_pflag = 0;
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pt, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA_TRY(ctx, cudaMemcpyAsync(&h_pflag, pflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_TRY(end_call_check_flag(ctx));
+  if (h_pflag) return fail(ctx, MYZKP_ERR_NONCANONICAL, "point coordinate >= p");
+  return MYZKP_OK;
 }
 
 int myzkp_fr_eval(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n, const uint8_t u_le[32], uint8_t out_y[32]) {

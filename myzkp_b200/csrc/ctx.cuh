@@ -90,6 +90,7 @@ struct myzkp_ctx {
   mz::DevBuf scalars2;     // quotient / folded coefficients
   mz::DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
   mz::DevBuf sort_parts;   // partition plan of the MSD split (msm.cu, sort.cu)
+  mz::DevBuf caller_points;  // Montgomery copies of caller-supplied points (myzkp_g1_msm)
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
   mz::DevBuf heads2;       // ping-pong levels of the head merge
@@ -136,7 +137,7 @@ namespace mz {
 template <class F>
 inline void for_each_scratch(myzkp_ctx* ctx, F f) {
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->sort_parts, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->sort_tmp, &ctx->sort_parts, &ctx->caller_points, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
                     &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
                     &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
   for (DevBuf* b : bufs) f(b);
@@ -191,7 +192,13 @@ struct MsmItem {
   size_t n;
 };
 int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K);
-int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets);
+int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
+                           bool per_window = false);
+// sum_i scalars[i] * points[i] for caller-supplied points (Montgomery affine on the device), no table of
+// multiples: per-window buckets + Horner over the windows
+int msm_points_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, const Affine* d_points_mont, size_t n, XYZZ* d_out);
+// canonical 64-byte affine points (device) -> Montgomery affine; ORs 1 into *d_flag for a coordinate >= p
+int points_import(myzkp_ctx* ctx, const uint32_t* d_in, size_t n, Affine* d_out, int* d_flag);
 int msm_batch_xyzz(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, XYZZ* d_out);
 // XYZZ (device) -> canonical affine 64 B (device)
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64);
@@ -209,7 +216,8 @@ int baa_accumulate(myzkp_ctx* ctx, const uint32_t* keys_s, const uint32_t* vals_
 // ---- sort.cu ----
 // LSD radix sort of (key, val) pairs by the low `bits` key bits; result in (*out_keys, *out_vals)
 int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
-                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts = nullptr, int P = 0);
+                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts = nullptr, int P = 0,
+                     bool first_pass_unordered = false);
 
 // ---- srs.cu ----
 int srs_alloc(myzkp_ctx* ctx, size_t n);

@@ -40,6 +40,22 @@ __device__ __forceinline__ Affine load_affine(const Affine* p) {
   r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
   return r;
 }
+// the same with an L2 fetch-size hint of 64 bytes (experiment: a 64-byte gather pulls a 128-byte line from HBM)
+__device__ __forceinline__ uint4 ldg_l2_64(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Affine load_affine_64(const Affine* p) {
+  Affine r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = ldg_l2_64(q), b = ldg_l2_64(q + 1), c = ldg_l2_64(q + 2), d = ldg_l2_64(q + 3);
+  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
+  r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
+  r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  return r;
+}
 __device__ __forceinline__ void store_xyzz(XYZZ* p, const XYZZ& v) {
   uint4* q = reinterpret_cast<uint4*>(p);
   const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
@@ -79,7 +95,8 @@ struct RecodeDesc {
 __global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const RecodeDesc* __restrict__ descs, int c, int W,
                                                   const uint8_t* __restrict__ row_of_bit, uint32_t srs_n,
                                                   uint32_t srs_off, uint32_t sentinel_key, uint32_t* __restrict__ keys_all,
-                                                  uint32_t* __restrict__ vals_all, int* __restrict__ flag) {
+                                                  uint32_t* __restrict__ vals_all, int* __restrict__ flag,
+                                                  uint32_t win_stride) {
   const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;  // a batch of one needs no descriptor upload
   const uint32_t* __restrict__ scalars = dsc.scalars;
   const size_t n = dsc.n;
@@ -111,8 +128,10 @@ __global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const Recod
     uint32_t neg = d > half ? 1u : 0u;
     uint32_t mag = neg ? ((1u << c) - d) : d;
     carry = neg;
-    uint32_t key = mag ? dsc.key_base + mag - 1 : sentinel_key;
-    uint32_t idx = (uint32_t)row_of_bit[bit] * srs_n + srs_off + (uint32_t)i;
+    // win_stride != 0: plain points without a table of multiples - every window owns its bucket range and
+    // reads row 0; the window weights 2^(c w) are applied after the bucket reduce (msm_window_combine)
+    uint32_t key = mag ? dsc.key_base + (uint32_t)w * win_stride + mag - 1 : sentinel_key;
+    uint32_t idx = (win_stride ? 0u : (uint32_t)row_of_bit[bit] * srs_n) + srs_off + (uint32_t)i;
     keys[(size_t)w * n + i] = key;
     vals[(size_t)w * n + i] = idx | (neg << 31);
   }
@@ -127,43 +146,40 @@ __global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const Recod
 // low_bits remain for the sort, which then runs inside each partition (sort.cu, locate_tile).
 //   msm_recode_count    per-partition entry counts (shared-memory counters, one global add per block and bin)
 //   msm_partition_plan  partition bases, tile bases, zeroed cursors (one block)
-//   msm_recode_scatter  recodes again, groups the block's entries by partition in shared memory, reserves
-//                       room in every partition with one atomic add each and copies the runs out
+//   msm_recode_scatter  recodes (digits stay in registers), groups the block's entries by partition in shared
+//                       memory, reserves room in every partition with one atomic add each, copies the runs out
 // Order inside a partition is arbitrary (bucket sums commute); the sort passes that follow are stable.
 constexpr int kMaxParts = 260;
-constexpr int kPartCap = 6144;  // entries staged per block (48 KB of keys + values)
 // device layout of ctx->sort_parts (uint32): part_base[P+1] | tile_start[P+1] | counts[P] | cursor[P]
 constexpr int kSortTileEntries = 4096;  // = kSortTile of sort.cu
 
-struct RecodeCtl {
-  int c, W, low_bits, P;
-  uint32_t srs_n, srs_off, sentinel_key;
+// row index of the table row holding 2^(c w) P for window w (kernel parameter: lives in the constant bank)
+struct RecodeRows {
+  uint8_t row[64];
 };
 
-// digits of one scalar, least significant window first: f(w, key, val)
-template <class F>
-__device__ __forceinline__ void recode_scalar(const Fr& sc, const RecodeCtl& ctl, uint32_t key_base,
-                                              const uint8_t* __restrict__ row_of_bit, uint32_t i, F f) {
-  const int c = ctl.c;
-  const uint32_t half = 1u << (c - 1);
-  const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+// digits of one scalar, least significant window first: f(w, key, sign).  C is a compile-time window so
+// the loop unrolls and every shift is an immediate (the run-time version costs ~60 instructions per digit).
+template <int C, class F>
+__device__ __forceinline__ void recode_digits(const Fr& sc, uint32_t key_base, uint32_t sentinel_key, F f) {
+  constexpr int W = (255 + C - 1) / C;
+  constexpr uint32_t half = 1u << (C - 1);
+  constexpr uint32_t mask = (1u << C) - 1u;
   uint32_t carry = 0;
-  for (int w = 0; w < ctl.W; w++) {
-    const int bit = w * c;
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const int bit = w * C;
     const int limb = bit >> 5, sh = bit & 31;
     uint32_t raw = 0;
     if (limb < 8) {
-      uint64_t two = sc.v[limb];
-      if (limb + 1 < 8) two |= (uint64_t)sc.v[limb + 1] << 32;
-      raw = (uint32_t)(two >> sh) & mask;
+      if (sh + C <= 32 || limb + 1 >= 8) raw = (sc.v[limb] >> sh) & mask;
+      else raw = __funnelshift_r(sc.v[limb], sc.v[limb + 1], sh) & mask;
     }
     const uint32_t d = raw + carry;
     const uint32_t neg = d > half ? 1u : 0u;
-    const uint32_t mag = neg ? ((1u << c) - d) : d;
+    const uint32_t mag = neg ? ((1u << C) - d) : d;
     carry = neg;
-    const uint32_t key = mag ? key_base + mag - 1 : ctl.sentinel_key;
-    const uint32_t idx = (uint32_t)row_of_bit[bit] * ctl.srs_n + ctl.srs_off + i;
-    f(w, key, idx | (neg << 31));
+    f(w, mag ? key_base + mag - 1 : sentinel_key, neg);
   }
 }
 __device__ __forceinline__ Fr load_scalar(const uint32_t* scalars, size_t i) {
@@ -175,23 +191,29 @@ __device__ __forceinline__ Fr load_scalar(const uint32_t* scalars, size_t i) {
   return sc;
 }
 
-// grid (blocks over the longest polynomial, K); every block handles `per_block` scalars
+struct RecodeCtl {
+  int low_bits, P;
+  uint32_t srs_n, srs_off, sentinel_key;
+};
+constexpr int kPartScalars = 512;  // scalars per block of the partitioned recode (2 per thread)
+
+// grid (blocks of kPartScalars scalars over the longest polynomial, K)
+template <int C>
 __global__ void __launch_bounds__(256) msm_recode_count(RecodeDesc single, const RecodeDesc* __restrict__ descs,
-                                                        RecodeCtl ctl, uint32_t per_block,
-                                                        const uint8_t* __restrict__ row_of_bit,
-                                                        uint32_t* __restrict__ counts, int* __restrict__ flag) {
+                                                        RecodeCtl ctl, uint32_t* __restrict__ counts,
+                                                        int* __restrict__ flag) {
   __shared__ uint32_t h[kMaxParts];
   const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;
   for (int p = threadIdx.x; p < ctl.P; p += blockDim.x) h[p] = 0;
   __syncthreads();
-  const size_t lo = (size_t)blockIdx.x * per_block;
-  const size_t hi = lo + per_block < dsc.n ? lo + per_block : dsc.n;
+  const size_t lo = (size_t)blockIdx.x * kPartScalars;
+  const size_t hi = lo + kPartScalars < dsc.n ? lo + kPartScalars : dsc.n;
   bool bad = false;
   for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const Fr sc = load_scalar(dsc.scalars, i);
     bad |= !fe_is_canonical(sc);
-    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i,
-                  [&](int, uint32_t key, uint32_t) { atomicAdd(&h[key >> ctl.low_bits], 1u); });
+    recode_digits<C>(sc, dsc.key_base, ctl.sentinel_key,
+                     [&](int, uint32_t key, uint32_t) { atomicAdd(&h[key >> ctl.low_bits], 1u); });
   }
   if (bad) atomicOr(flag, 1);
   __syncthreads();
@@ -219,41 +241,74 @@ __global__ void msm_partition_plan(uint32_t* __restrict__ parts, int P) {
   for (int p = threadIdx.x; p < P; p += blockDim.x) cursor[p] = 0;
 }
 
+// Every thread recodes its two scalars ONCE into registers; the block then groups the entries by partition
+// in shared memory and copies each partition's run to the room it reserved with one atomic add.
+template <int C>
 __global__ void __launch_bounds__(256) msm_recode_scatter(RecodeDesc single, const RecodeDesc* __restrict__ descs,
-                                                          RecodeCtl ctl, uint32_t per_block,
-                                                          const uint8_t* __restrict__ row_of_bit,
-                                                          uint32_t* __restrict__ parts, uint32_t* __restrict__ keys_out,
-                                                          uint32_t* __restrict__ vals_out) {
-  extern __shared__ uint32_t stage[];  // keys[kPartCap] | vals[kPartCap]
+                                                          RecodeCtl ctl, RecodeRows rows, uint32_t* __restrict__ parts,
+                                                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  constexpr int W = (255 + C - 1) / C;
+  constexpr int kPer = kPartScalars / 256;
+  extern __shared__ uint32_t stage[];  // keys[kPartScalars * W] | vals[kPartScalars * W]
   __shared__ uint32_t h[kMaxParts];      // counts, then running local cursors
   __shared__ uint32_t loc_off[kMaxParts + 1];
   __shared__ uint32_t gbase[kMaxParts];
+  __shared__ uint32_t ws[33];
   uint32_t* s_keys = stage;
-  uint32_t* s_vals = stage + kPartCap;
+  uint32_t* s_vals = stage + kPartScalars * W;
   const RecodeDesc dsc = descs ? descs[blockIdx.y] : single;
   const int P = ctl.P;
   const uint32_t* part_base = parts;
   uint32_t* cursor = parts + 2 * (P + 1) + P;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) h[p] = 0;
+  for (int p = threadIdx.x; p < kMaxParts; p += blockDim.x) h[p] = 0;
   __syncthreads();
-  const size_t lo = (size_t)blockIdx.x * per_block;
-  const size_t hi = lo + per_block < dsc.n ? lo + per_block : dsc.n;
-  if (lo >= hi) return;
-  // sweep 1: counts
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const Fr sc = load_scalar(dsc.scalars, i);
-    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i,
-                  [&](int, uint32_t key, uint32_t) { atomicAdd(&h[key >> ctl.low_bits], 1u); });
+  const size_t lo = (size_t)blockIdx.x * kPartScalars;
+  if (lo >= dsc.n) return;
+  uint32_t keys_r[kPer][W], vals_r[kPer][W];
+#pragma unroll
+  for (int s = 0; s < kPer; s++) {
+    const size_t i = lo + (size_t)s * 256 + threadIdx.x;
+    if (i < dsc.n) {
+      const Fr sc = load_scalar(dsc.scalars, i);
+      recode_digits<C>(sc, dsc.key_base, ctl.sentinel_key, [&](int w, uint32_t key, uint32_t neg) {
+        keys_r[s][w] = key;
+        vals_r[s][w] = ((uint32_t)rows.row[w] * ctl.srs_n + ctl.srs_off + (uint32_t)i) | (neg << 31);
+        atomicAdd(&h[key >> ctl.low_bits], 1u);
+      });
+    } else {
+#pragma unroll
+      for (int w = 0; w < W; w++) keys_r[s][w] = 0xffffffffu;  // no entry
+    }
   }
   __syncthreads();
-  // local offsets (P is small: one thread), global reservations
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int p = 0; p < P; p++) {
-      loc_off[p] = run;
-      run += h[p];
+  // exclusive scan of the partition counts (P <= kMaxParts <= 2 x 256: two bins per thread)
+  {
+    const int p0 = 2 * threadIdx.x, p1 = p0 + 1;
+    const uint32_t c0 = p0 < P ? h[p0] : 0u, c1 = p1 < P ? h[p1] : 0u;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
     }
-    loc_off[P] = run;
+    if (lane == 31) ws[wrp] = incl;
+    __syncthreads();
+    if (wrp == 0) {
+      uint32_t v = lane < 8 ? ws[lane] : 0u, sc = v;
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, sc, d);
+        if (lane >= d) sc += o;
+      }
+      if (lane < 8) ws[lane] = sc - v;
+      if (lane == 7) ws[32] = sc;
+    }
+    __syncthreads();
+    const uint32_t ex = ws[wrp] + incl - (c0 + c1);
+    if (p0 < P) loc_off[p0] = ex;
+    if (p1 < P) loc_off[p1] = ex + c0;
+    if (threadIdx.x == 0) loc_off[P] = ws[32];
   }
   __syncthreads();
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
@@ -262,14 +317,17 @@ __global__ void __launch_bounds__(256) msm_recode_scatter(RecodeDesc single, con
     h[p] = loc_off[p];  // becomes the running local cursor
   }
   __syncthreads();
-  // sweep 2: place
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const Fr sc = load_scalar(dsc.scalars, i);
-    recode_scalar(sc, ctl, dsc.key_base, row_of_bit, (uint32_t)i, [&](int, uint32_t key, uint32_t val) {
-      const uint32_t pos = atomicAdd(&h[key >> ctl.low_bits], 1u);
-      s_keys[pos] = key;
-      s_vals[pos] = val;
-    });
+#pragma unroll
+  for (int s = 0; s < kPer; s++) {
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+      const uint32_t key = keys_r[s][w];
+      if (key != 0xffffffffu) {
+        const uint32_t pos = atomicAdd(&h[key >> ctl.low_bits], 1u);
+        s_keys[pos] = key;
+        s_vals[pos] = vals_r[s][w];
+      }
+    }
   }
   __syncthreads();
   const uint32_t total = loc_off[P];
@@ -282,6 +340,27 @@ __global__ void __launch_bounds__(256) msm_recode_scatter(RecodeDesc single, con
   }
 }
 
+template <int C>
+static int launch_partitioned_recode(myzkp_ctx* ctx, const RecodeDesc& single, const RecodeDesc* d_descs, size_t K, size_t n,
+                                     const RecodeCtl& ctl, const RecodeRows& rows, uint32_t* parts, uint32_t* counts,
+                                     uint32_t* keys_a, uint32_t* vals_a, int* flag) {
+  constexpr int W = (255 + C - 1) / C;
+  constexpr int smem = 2 * kPartScalars * W * (int)sizeof(uint32_t);
+  const unsigned gx = (unsigned)((n + kPartScalars - 1) / kPartScalars);
+  msm_recode_count<C><<<dim3(gx, (unsigned)K), 256, 0, ctx->stream>>>(single, d_descs, ctl, counts, flag);
+  MZ_LAUNCH_CHECK(ctx);
+  msm_partition_plan<<<1, 256, 0, ctx->stream>>>(parts, ctl.P);
+  MZ_LAUNCH_CHECK(ctx);
+  static bool attr_set[64] = {};
+  if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
+    MZ_CUDA_TRY(ctx, cudaFuncSetAttribute(msm_recode_scatter<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[ctx->device] = true;
+  }
+  msm_recode_scatter<C><<<dim3(gx, (unsigned)K), 256, smem, ctx->stream>>>(single, d_descs, ctl, rows, parts, keys_a, vals_a);
+  MZ_LAUNCH_CHECK(ctx);
+  return MYZKP_OK;
+}
+
 // ---------------------------------------------------------------------------
 // 3. segment accumulate
 // ---------------------------------------------------------------------------
@@ -291,6 +370,7 @@ __global__ void __launch_bounds__(256) msm_recode_scatter(RecodeDesc single, con
 // unique first writer of that bucket.  Buckets are pre-zeroed (= infinity).
 constexpr int kAccThreads = 128;
 
+template <bool kHint64>
 __global__ void __launch_bounds__(kAccThreads, 4)
     msm_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M, uint32_t L,
                    uint32_t sentinel, const Affine* __restrict__ tbl, XYZZ* __restrict__ buckets,
@@ -309,7 +389,7 @@ __global__ void __launch_bounds__(kAccThreads, 4)
   bool first_run = true;
   // software pipeline: the next entry's point is in flight while this one is added
   uint32_t v = vals[s];
-  Affine pt = load_affine(tbl + (v & 0x7fffffffu));
+  Affine pt = kHint64 ? load_affine_64(tbl + (v & 0x7fffffffu)) : load_affine(tbl + (v & 0x7fffffffu));
   for (uint64_t i = s; i < e; i++) {
     uint32_t k_next = sentinel, v_next = 0;
     Affine pt_next;
@@ -318,7 +398,7 @@ __global__ void __launch_bounds__(kAccThreads, 4)
       k_next = keys[i + 1];
       if (k_next < sentinel) {
         v_next = vals[i + 1];
-        pt_next = load_affine(tbl + (v_next & 0x7fffffffu));
+        pt_next = kHint64 ? load_affine_64(tbl + (v_next & 0x7fffffffu)) : load_affine(tbl + (v_next & 0x7fffffffu));
       }
     }
     if (v >> 31) pt.y = fe_neg(pt.y);
@@ -730,21 +810,24 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
 // pipeline: polynomial y owns the bucket range [y nb, (y+1) nb) of `buckets` (K 2^(c-1) XYZZ), so one
 // sort, one accumulate and one merge serve the whole batch - many small commitments cost their
 // entries, not K latency-bound pipelines.
-int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets) {
+int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
+                           bool per_window) {
   if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
-  if (c < 1 || c > 24 || !((ctx->windows >> c) & 1)) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
+  if (c < 1 || c > 24 || (!per_window && !((ctx->windows >> c) & 1)))
+    return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
   if (K == 0 || K > 65535) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch of 1..65535 polynomials");
   const int W = (255 + c - 1) / c;
   const uint32_t nb1 = 1u << (c - 1);
-  if ((uint64_t)K * nb1 >= (1ull << 32) - 1) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch needs more than 2^32 buckets");
-  const uint32_t nb = (uint32_t)K * nb1;  // buckets of the whole batch; also the sentinel key
+  const uint64_t sets = (uint64_t)K * (per_window ? (uint64_t)W : 1u);  // bucket sets of nb1 buckets each
+  if (sets * nb1 >= (1ull << 32) - 1) return fail(ctx, MYZKP_ERR_INVALID_ARG, "batch needs more than 2^32 buckets");
+  const uint32_t nb = (uint32_t)(sets * nb1);  // buckets of the whole batch; also the sentinel key
   uint64_t M = 0;
   size_t n = 0;  // longest polynomial
   std::vector<RecodeDesc> descs(K);
   for (size_t y = 0; y < K; y++) {
     if (srs_off + items[y].n > ctx->srs_n)
       return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
-    descs[y] = RecodeDesc{items[y].d_scalars, items[y].n, M, (uint32_t)y * nb1, 0};
+    descs[y] = RecodeDesc{items[y].d_scalars, items[y].n, M, (uint32_t)(y * (per_window ? (uint64_t)W : 1u)) * nb1, 0};
     M += (uint64_t)W * items[y].n;
     if (items[y].n > n) n = items[y].n;
   }
@@ -777,10 +860,10 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
     MZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->descs.p, descs.data(), K * sizeof(RecodeDesc), cudaMemcpyHostToDevice, ctx->stream));
     d_descs = ctx->descs.as<RecodeDesc>();
   }
-  // MSD split inside the recode when the key has more than 16 bits: the sort then only handles the low 16
-  // (or 24) bits, inside each partition
+  // MSD split inside the recode when the key has more than 16 bits (windows 20, 22, 24: the recode kernels are
+  // compiled per window): the sort then only handles the low 16 (or 24) bits, inside each partition
   int low_bits = 0, P = 0;
-  if (sort_bits > 16 && !getenv("MZ_NO_PARTITION")) {
+  if (sort_bits > 16 && !per_window && (c == 20 || c == 22 || c == 24) && !getenv("MZ_NO_PARTITION")) {
     low_bits = 16;
     if (((uint64_t)nb >> low_bits) + 1 > (uint64_t)(kMaxParts - 3)) low_bits = 24;
     if (sort_bits > low_bits) P = (int)(((uint64_t)nb >> low_bits) + 1);
@@ -788,32 +871,21 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   }
   const uint32_t* d_parts = nullptr;
   if (n && P) {
-    RecodeCtl ctl{c, W, low_bits, P, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb};
+    RecodeCtl ctl{low_bits, P, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb};
+    RecodeRows rows;
+    for (int w = 0; w < 64; w++) rows.row[w] = w < W ? ctx->row_of_bit[w * c] : 0;
     MZ_CUDA_TRY(ctx, ctx->sort_parts.ensure((size_t)(4 * P + 8) * sizeof(uint32_t)));
     uint32_t* parts = ctx->sort_parts.as<uint32_t>();
     uint32_t* counts = parts + 2 * (P + 1);
     MZ_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)P * sizeof(uint32_t), ctx->stream));
-    uint32_t per_block = (uint32_t)(kPartCap / W);
-    if (per_block < 1) return fail(ctx, MYZKP_ERR_INVALID_ARG, "window too small for the partitioned recode");
-    const unsigned gx = (unsigned)((n + per_block - 1) / per_block);
-    msm_recode_count<<<dim3(gx, (unsigned)K), 256, 0, ctx->stream>>>(descs[0], d_descs, ctl, per_block, ctx->d_row_of_bit,
-                                                                      counts, flag);
-    MZ_LAUNCH_CHECK(ctx);
-    msm_partition_plan<<<1, 256, 0, ctx->stream>>>(parts, P);
-    MZ_LAUNCH_CHECK(ctx);
-    static bool attr_set[64] = {};
-    if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
-      MZ_CUDA_TRY(ctx, cudaFuncSetAttribute(msm_recode_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            2 * kPartCap * (int)sizeof(uint32_t)));
-      attr_set[ctx->device] = true;
-    }
-    msm_recode_scatter<<<dim3(gx, (unsigned)K), 256, 2 * kPartCap * sizeof(uint32_t), ctx->stream>>>(
-        descs[0], d_descs, ctl, per_block, ctx->d_row_of_bit, parts, keys_a, vals_a);
-    MZ_LAUNCH_CHECK(ctx);
+    if (c == 20) MZ_TRY(launch_partitioned_recode<20>(ctx, descs[0], d_descs, K, n, ctl, rows, parts, counts, keys_a, vals_a, flag));
+    else if (c == 22) MZ_TRY(launch_partitioned_recode<22>(ctx, descs[0], d_descs, K, n, ctl, rows, parts, counts, keys_a, vals_a, flag));
+    else MZ_TRY(launch_partitioned_recode<24>(ctx, descs[0], d_descs, K, n, ctl, rows, parts, counts, keys_a, vals_a, flag));
     d_parts = parts;
   } else if (n) {
     msm_recode<<<dim3((unsigned)((n + 255) / 256), (unsigned)K), 256, 0, ctx->stream>>>(
-        descs[0], d_descs, c, W, ctx->d_row_of_bit, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb, keys_a, vals_a, flag);
+        descs[0], d_descs, c, W, ctx->d_row_of_bit, (uint32_t)ctx->srs_n, (uint32_t)srs_off, nb, keys_a, vals_a, flag,
+        per_window ? nb1 : 0u);
     MZ_LAUNCH_CHECK(ctx);
   }
 
@@ -821,7 +893,7 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit; only the low bits when partitioned)
   uint32_t *keys_s = nullptr, *vals_s = nullptr;
   MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, d_parts ? low_bits : sort_bits, &keys_s, &vals_s,
-                          d_parts, P));
+                          d_parts, P, !getenv("MZ_SORT_STABLE")));
 
   // 3. accumulate
   // Segment length: enough segments to fill the GPU several times over, but not much
@@ -874,8 +946,13 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
     MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, buckets, ctx->heads.as<XYZZ>(),
                           ctx->head_keys.as<uint32_t>(), T));
   } else {
-    msm_accumulate<<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-        keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+    static const bool hint64 = getenv("MZ_GATHER_L2_64B") != nullptr;  // experiment knob
+    if (hint64)
+      msm_accumulate<true><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+    else
+      msm_accumulate<false><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
     MZ_LAUNCH_CHECK(ctx);
   }
 
@@ -943,6 +1020,61 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
   ctx->phase_pending = false;
   ctx->msm_count++;
   return MYZKP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// MSM over caller-supplied points, without a table of multiples (accumulate_curve_points,
+// zksnark/utils.rs:83-93): classic windowed Pippenger.  Window w has its own bucket range, the pipeline
+// above produces S_w = sum_k k B_{w,k} for every window, and out = sum_w 2^(c w) S_w by Horner from the
+// top window (c doublings + one addition per window; ~254 dependent doublings, about a millisecond of
+// latency, independent of n).
+// ---------------------------------------------------------------------------
+__global__ void msm_window_combine(const XYZZ* __restrict__ sums, int W, int c, XYZZ* __restrict__ out) {
+  XYZZ acc = load_xyzz(sums + (W - 1));
+  for (int w = W - 2; w >= 0; w--) {
+    for (int k = 0; k < c; k++) xyzz_dbl(acc);
+    XYZZ sw = load_xyzz(sums + w);
+    xyzz_add(acc, sw);
+  }
+  store_xyzz(out, acc);
+}
+
+int msm_points_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, const Affine* d_points_mont, size_t n, XYZZ* d_out) {
+  if (n == 0) {
+    xyzz_set_inf<<<1, 1, 0, ctx->stream>>>(d_out);
+    MZ_LAUNCH_CHECK(ctx);
+    return MYZKP_OK;
+  }
+  // window by work: W(c) n mixed additions (10 multiplies) + W(c) 2^(c-1) buckets x 2 additions (28)
+  int c = 8;
+  {
+    double best = 0;
+    for (int cc = 4; cc <= 20; cc++) {
+      const int Wc = (255 + cc - 1) / cc;
+      const double cost = 10.0 * Wc * (double)n + 28.0 * Wc * (double)((size_t)1 << (cc - 1));
+      if (best == 0 || cost < best) { best = cost; c = cc; }
+    }
+  }
+  const int W = (255 + c - 1) / c;
+  const size_t nbw = (size_t)W << (c - 1);
+  // the pipeline reads points through ctx->table / srs_n: point it at the caller's points for this call
+  Affine* saved_table = ctx->table;
+  const size_t saved_n = ctx->srs_n;
+  ctx->table = const_cast<Affine*>(d_points_mont);
+  ctx->srs_n = n;
+  int rc = [&]() -> int {
+    MZ_CUDA_TRY(ctx, ctx->buckets.ensure(nbw * sizeof(XYZZ)));
+    MZ_CUDA_TRY(ctx, ctx->xyzz_tmp.ensure((size_t)(W + 2) * sizeof(XYZZ)));
+    MsmItem one{d_scalars, n};
+    MZ_TRY(msm_fill_buckets_batch(ctx, &one, 1, 0, c, ctx->buckets.as<XYZZ>(), /*per_window=*/true));
+    MZ_TRY(msm_reduce_buckets(ctx, c, ctx->buckets.as<XYZZ>(), ctx->xyzz_tmp.as<XYZZ>(), (size_t)W));
+    msm_window_combine<<<1, 1, 0, ctx->stream>>>(ctx->xyzz_tmp.as<XYZZ>(), W, c, d_out);
+    MZ_LAUNCH_CHECK(ctx);
+    return MYZKP_OK;
+  }();
+  ctx->table = saved_table;
+  ctx->srs_n = saved_n;
+  return rc;
 }
 
 int xyzz_to_bytes(myzkp_ctx* ctx, const XYZZ* d_in, size_t count, uint8_t* d_out64) {

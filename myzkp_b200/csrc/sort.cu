@@ -189,10 +189,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) atomicAdd(&h[(k[i] >> shift) & (kRadix - 1)], 1u);
   } else {
+    // partial or unaligned tile (partitions start anywhere): scalar loads, still all issued before the atomics
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
       uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
-      if (p < ref.count) atomicAdd(&h[(keys[base + p] >> shift) & (kRadix - 1)], 1u);
+      k[i] = p < ref.count ? __ldg(keys + base + p) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      uint32_t p = (uint32_t)i * kSortThreads + threadIdx.x;
+      if (p < ref.count) atomicAdd(&h[(k[i] >> shift) & (kRadix - 1)], 1u);
     }
   }
   __syncthreads();
@@ -202,6 +208,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
 // Persistent: each block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile's keys,
 // values and digit bases are fetched into registers before the current tile is ranked, so the
 // DRAM latency is covered by the ranking work rather than by occupancy.
+// kStable = false: entries of equal digit may leave in any order (allowed for a pass whose input order carries
+// no information - the first pass after the recode): ranks come from one shared-memory atomic per entry
+// instead of the ballot match and the per-warp counters, about a third of the instructions.
+template <bool kStable>
 __global__ void __launch_bounds__(kSortThreads, 2)
     sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
                       const uint32_t* __restrict__ hist_scanned, uint32_t ntiles_arg, uint32_t* __restrict__ keys_out,
@@ -248,29 +258,38 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
     gbase[threadIdx.x] = gb;
     __syncthreads();
-    // all 16 matches first (they only depend on the keys, so they pipeline), then the
-    // sequential per-warp counter updates
+    if (kStable) {
+      // all 16 matches first (they only depend on the keys, so they pipeline), then the
+      // sequential per-warp counter updates
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
-      uint32_t p = wbase + i * 32 + lane;
-      uint32_t d = (k[i] >> shift) & (kRadix - 1);
-      rank[i] = warp_match_digit(d, p < tile_n);  // peers: lanes of this warp with the same digit in this round
-    }
-#pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
-      uint32_t p = wbase + i * 32 + lane;
-      bool ok = p < tile_n;
-      uint32_t d = (k[i] >> shift) & (kRadix - 1);
-      uint32_t peers = rank[i];
-      uint32_t before = __popc(peers & ((1u << lane) - 1u));
-      uint32_t prev = 0;
-      if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter
-        prev = cnt[w][d];
-        cnt[w][d] = prev + __popc(peers);
+      for (int i = 0; i < kSortItems; i++) {
+        uint32_t p = wbase + i * 32 + lane;
+        uint32_t d = (k[i] >> shift) & (kRadix - 1);
+        rank[i] = warp_match_digit(d, p < tile_n);  // peers: lanes of this warp with the same digit in this round
       }
-      prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-      rank[i] = prev + before;
-      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < kSortItems; i++) {
+        uint32_t p = wbase + i * 32 + lane;
+        bool ok = p < tile_n;
+        uint32_t d = (k[i] >> shift) & (kRadix - 1);
+        uint32_t peers = rank[i];
+        uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t prev = 0;
+        if (ok && before == 0) {  // lowest lane of the peer group bumps the warp counter
+          prev = cnt[w][d];
+          cnt[w][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+        rank[i] = prev + before;
+        __syncwarp();
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSortItems; i++) {
+        uint32_t p = wbase + i * 32 + lane;
+        uint32_t d = (k[i] >> shift) & (kRadix - 1);
+        rank[i] = p < tile_n ? atomicAdd(&cnt[0][d], 1u) : 0u;
+      }
     }
     __syncthreads();
     // digit totals -> exclusive scan over digits -> per-warp bases
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
       uint32_t p = wbase + i * 32 + lane;
       if (p < tile_n) {
         uint32_t d = (k[i] >> shift) & (kRadix - 1);
-        uint32_t pos = cnt[w][d] + rank[i];
+        uint32_t pos = cnt[kStable ? w : 0][d] + rank[i];
         s_keys[pos] = k[i];
         s_vals[pos] = v[i];
       }
@@ -323,10 +342,13 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 // ---------------------------------------------------------------------------
 // Sorts n (key, val) pairs by the low `bits` key bits.  The result lands in
 // (*out_keys, *out_vals), which alias either the a- or the b-buffers.
+// first_pass_unordered: the caller does not care about the order of equal keys (the MSM does not), so the
+// first pass may be unstable; the later passes are always stable, as LSD radix sort needs.
 // d_parts / P (optional): the list is already split into P partitions by its high key bits (layout in the
 // comment above locate_tile); each partition is then sorted on its own by the low `bits` bits.
 int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
-                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts, int P) {
+                     int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts, int P,
+                     bool first_pass_unordered) {
   *out_keys = keys_a;
   *out_vals = vals_a;
   if (n == 0 || bits <= 0) return MYZKP_OK;
@@ -351,7 +373,10 @@ int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_
     scan_apply<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums);
     MZ_LAUNCH_CHECK(ctx);
     const uint32_t sblocks = ntiles < (uint32_t)ctx->sm_count * 2 ? ntiles : (uint32_t)ctx->sm_count * 2;
-    sort_tile_scatter<<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+    if (shift == 0 && first_pass_unordered)
+      sort_tile_scatter<false><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+    else
+      sort_tile_scatter<true><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
     MZ_LAUNCH_CHECK(ctx);
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;

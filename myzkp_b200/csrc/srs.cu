@@ -222,6 +222,13 @@ int srs_build_from_row0(myzkp_ctx* ctx) {
   return MYZKP_OK;
 }
 
+int points_import(myzkp_ctx* ctx, const uint32_t* d_in, size_t n, Affine* d_out, int* d_flag) {
+  if (n == 0) return MYZKP_OK;
+  srs_import<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, n, d_out, d_flag);
+  MZ_LAUNCH_CHECK(ctx);
+  return MYZKP_OK;
+}
+
 static int ensure_gcomb(myzkp_ctx* ctx) {
   if (ctx->gcomb) return MYZKP_OK;
   // base2[j] = 2^(8j) G through the same row builder (n = 1)

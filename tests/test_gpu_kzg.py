@@ -518,6 +518,24 @@ def test_generic_msm_with_caller_points(ctx):
     coefs = [rnd.randrange(R) for _ in range(64)]
     assert ctx.srs_len == 64
     assert ctx.g1_msm(coefs) == o.expected_commit(coefs, alpha) == ctx.commit(coefs)
+    # a large call: the points are an SRS read back from the device, so the expected value is the commitment;
+    # windowed Pippenger without a table (per-window buckets + Horner over the windows) at two window choices
+    for n in (5000, 70000):
+        ctx.srs_generate(alpha, n)
+        big_pts = ctx.srs_read(0, n)
+        big_sc = synth.limbs_to_ints(synth.random_scalars(n, 900 + n))
+        big_sc[7] = 0
+        big_sc[8] = R - 1
+        ctx.srs_generate(alpha, 8)  # a different resident SRS: the call must not use (or disturb) it
+        assert ctx.g1_msm(big_sc, big_pts) == o.expected_commit(big_sc, alpha)
+        assert ctx.srs_len == 8
+    # error behaviour: coordinate >= p, scalar >= r
+    bad_pt = [(o.P_MOD, 2)] + big_pts[1:5]
+    with pytest.raises(mz.MyzkpError):
+        ctx.g1_msm([1, 2, 3, 4, 5], bad_pt)
+    bad_sc = synth.ints_to_limbs([1, 2, R, 4, 5])
+    with pytest.raises(mz.MyzkpError):
+        ctx.g1_msm(bad_sc, big_pts[:5])
 
 
 def test_g2_powers_of_the_public_key(ctx):

@@ -43,6 +43,8 @@ int begin_call(myzkp_ctx* ctx) {
 // Upload pipeline for the host-buffer entry points: how many chunks to split n into
 int upload_chunks(const myzkp_ctx* ctx, size_t n) {
   if (ctx->upload_chunks > 0) return (size_t)ctx->upload_chunks <= (n ? n : 1) ? ctx->upload_chunks : 1;
+  const char* e = getenv("MZ_UPLOAD_CHUNKS");  // experiment knob
+  if (e && atoi(e) > 0) return (size_t)atoi(e) <= (n ? n : 1) ? atoi(e) : 1;
   if (n >= ((size_t)1 << 24)) return 3;
   if (n >= ((size_t)1 << 21)) return 2;  // measured (scripts/upload_sweep.py): 2^21 6.35 vs 6.93 ms, 2^20 3.90 vs 3.95 ms
   return 1;
@@ -148,9 +150,8 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
   const size_t n_msm = u_le ? n - 1 : n;  // the quotient has one coefficient less
   const int c = msm_pick_window(ctx, n_msm);
   const size_t nb = (size_t)1 << (c - 1);
-  MZ_CUDA_TRY(ctx, ctx->buckets.ensure(2 * nb * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->buckets.ensure(nb * sizeof(XYZZ)));
   XYZZ* b0 = ctx->buckets.as<XYZZ>();
-  XYZZ* b1 = b0 + nb;
   bool first = true;
   for (int pos = 0; pos < K; pos++) {
     size_t lo, hi;
@@ -169,8 +170,8 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
       if (top) len -= 1;
     }
     if (len == 0) continue;
-    MZ_TRY(msm_fill_buckets(ctx, sc, len, srs_off + lo, c, first ? b0 : b1));
-    if (!first) MZ_TRY(msm_add_buckets(ctx, b0, b1, c));
+    // later chunks accumulate onto the same bucket set (msm_accumulate<kOnto>): no second set, no dense addition
+    MZ_TRY(msm_fill_buckets(ctx, sc, len, srs_off + lo, c, b0, /*onto=*/!first));
     first = false;
   }
   if (first) MZ_CUDA_TRY(ctx, cudaMemsetAsync(b0, 0, nb * sizeof(XYZZ), ctx->stream));
@@ -221,8 +222,7 @@ int myzkp_ctx_reserve(myzkp_ctx* ctx, size_t n_max) {
     const uint8_t zero[32] = {0};
     const size_t n_msm = n_max < ctx->srs_n ? n_max : ctx->srs_n;
     if (ctx->table && n_msm) {
-      // twice the buckets: the chunked upload pipeline accumulates into a second set
-      MZ_CUDA_TRY(ctx, ctx->buckets.ensure(2 * ((size_t)1 << (msm_pick_window(ctx, n_msm) - 1)) * sizeof(XYZZ)));
+      MZ_CUDA_TRY(ctx, ctx->buckets.ensure(((size_t)1 << (msm_pick_window(ctx, n_msm) - 1)) * sizeof(XYZZ)));
       MZ_TRY(msm_xyzz(ctx, ctx->scalars.as<uint32_t>(), n_msm, 0, reinterpret_cast<XYZZ*>(s + kSmallXyzz)));
     }
     if (n_max) {

@@ -182,7 +182,9 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 // the two halves of msm_xyzz, for callers that accumulate several scalar chunks into bucket sets of
 // the same window c before one final reduce (upload pipeline in capi.cu)
 int msm_pick_window(const myzkp_ctx* ctx, size_t n);
-int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets);
+// onto: add to what `buckets` already holds (the sums of earlier chunks) instead of overwriting it
+int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets,
+                     bool onto = false);
 int msm_add_buckets(myzkp_ctx* ctx, XYZZ* a, const XYZZ* b, int c);
 int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, size_t K = 1);
 // K polynomials as ONE pipeline (shared sort / accumulate / merge, bucket range y per polynomial):
@@ -193,7 +195,7 @@ struct MsmItem {
 };
 int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K);
 int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
-                           bool per_window = false);
+                           bool per_window = false, bool onto = false);
 // sum_i scalars[i] * points[i] for caller-supplied points (Montgomery affine on the device), no table of
 // multiples: per-window buckets + Horner over the windows
 int msm_points_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, const Affine* d_points_mont, size_t n, XYZZ* d_out);

@@ -370,7 +370,10 @@ static int launch_partitioned_recode(myzkp_ctx* ctx, const RecodeDesc& single, c
 // unique first writer of that bucket.  Buckets are pre-zeroed (= infinity).
 constexpr int kAccThreads = 128;
 
-template <bool kHint64>
+// kOnto: the buckets already hold the sums of earlier scalar chunks (upload pipeline): a run's unique writer
+// starts from the bucket's value instead of infinity, so no second bucket set and no dense bucket addition
+// are needed; runs that go to `heads` are folded in by the merge kernels, which read-modify-write anyway.
+template <bool kHint64, bool kOnto>
 __global__ void __launch_bounds__(kAccThreads, 4)
     msm_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M, uint32_t L,
                    uint32_t sentinel, const Affine* __restrict__ tbl, XYZZ* __restrict__ buckets,
@@ -407,9 +410,9 @@ __global__ void __launch_bounds__(kAccThreads, 4)
       if (first_run) store_xyzz(heads + t, acc);
       else store_xyzz(buckets + cur, acc);
       first_run = false;
-      acc = xyzz_inf();
       cur = k_next;
       if (k_next >= sentinel) break;
+      acc = kOnto ? load_xyzz(buckets + k_next) : xyzz_inf();
     }
     v = v_next;
     pt = pt_next;
@@ -801,9 +804,9 @@ int msm_batch_xyzz(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_of
 
 // steps 1-4: recode, sort, accumulate, merge -> `buckets` (2^(c-1) XYZZ, overwritten) holds the
 // bucket sums of sum_i scalars[i] * SRS[srs_off + i] for window c
-int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets) {
+int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, XYZZ* buckets, bool onto) {
   MsmItem one{d_scalars, n};
-  return msm_fill_buckets_batch(ctx, &one, 1, srs_off, c, buckets);
+  return msm_fill_buckets_batch(ctx, &one, 1, srs_off, c, buckets, false, onto);
 }
 
 // The same for a batch of K polynomials sharing the window c (each against SRS[srs_off ...]) in ONE
@@ -811,7 +814,7 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
 // sort, one accumulate and one merge serve the whole batch - many small commitments cost their
 // entries, not K latency-bound pipelines.
 int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
-                           bool per_window) {
+                           bool per_window, bool onto) {
   if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
   if (c < 1 || c > 24 || (!per_window && !((ctx->windows >> c) & 1)))
     return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
@@ -919,19 +922,20 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   }
   L += L & 1;  // even: the fused batched-affine accumulate reads (key, val) pairs as aligned 8-byte words
   if (M == 0) {  // nothing but empty polynomials: every bucket is the point at infinity
-    MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+    if (!onto) MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
     ctx->phase_pending = false;
     return MYZKP_OK;
   }
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
-  MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
+  if (!onto) MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(2);
   // Accumulate variants (myzkp_ctx_set_baa_rounds): 0 = XYZZ mixed additions only; -2 = fused batched-affine
   // pair sums (msm_accumulate_baa); -1 = automatic: fused when segments are long enough for the lane-private
   // batch inversion to amortise; 1..3 = the older multi-pass rounds (baa.cu, kept for comparison).
   int baa = ctx->baa_rounds;
+  if (onto) baa = 0;  // only the XYZZ kernel knows how to start from existing bucket values
   const bool fused = (baa == -2 && L >= 4) || (baa == -1 && L >= (uint32_t)kBaaAutoMinL);
   if (fused) {
     static const int minb = getenv("MZ_BAA_MINB") ? atoi(getenv("MZ_BAA_MINB")) : 4;  // experiment knob
@@ -947,11 +951,15 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
                           ctx->head_keys.as<uint32_t>(), T));
   } else {
     static const bool hint64 = getenv("MZ_GATHER_L2_64B") != nullptr;  // experiment knob
-    if (hint64)
-      msm_accumulate<true><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+    const unsigned blocks = (unsigned)((T + kAccThreads - 1) / kAccThreads);
+    if (onto)
+      msm_accumulate<false, true><<<blocks, kAccThreads, 0, ctx->stream>>>(
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+    else if (hint64)
+      msm_accumulate<true, false><<<blocks, kAccThreads, 0, ctx->stream>>>(
           keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
     else
-      msm_accumulate<false><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
+      msm_accumulate<false, false><<<blocks, kAccThreads, 0, ctx->stream>>>(
           keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
     MZ_LAUNCH_CHECK(ctx);
   }

@@ -1,6 +1,9 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel of the path at small sizes.
 usage: compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py [gemini_log2n]"""
+import os
 import sys
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # same-device emulated ranks: no lazy loads while a peer spins
 
 import numpy as np
 

@@ -1,6 +1,12 @@
 import os
 import sys
 
+# Several GPU tests run a few emulated ranks (one context each) on ONE device, whose exchange kernels spin on each
+# other.  With CUDA's default lazy module loading the first launch of a not-yet-loaded kernel synchronises the
+# device - inside that window it would wait for a spinning peer and run into the exchange time-out (seen when
+# a test subset is run with -k, so that earlier tests have not warmed the kernels).  Load everything up front.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

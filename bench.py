@@ -677,15 +677,19 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
     ex[f"quotient_scan_2^{log2n}_ms"] = ms_q
     ex["quotient_scan_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                     "frac": (gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
-                                    "note": "algorithmic 64 B/coefficient (read f, write q); the 3-kernel form moves 96 B"}
-    # the parallel scan spends ~2.5 Fr multiplies per coefficient (16-coefficient Horner runs twice + the
-    # Kogge-Stone steps), so the IMAD pipe, not HBM, is its nearer ceiling
+                                    "note": "algorithmic 64 B/coefficient (read f, write q); the single-pass look-back scan "
+                                            "moves exactly that (ncu: 537 MB read + 484 MB written at 2^24), but the kernel is "
+                                            "bound by its Fr multiplies, not by HBM - see quotient_scan_roofline_imad"}
+    # the parallel scan spends 2.75 Fr multiplies per coefficient (16-coefficient Horner twice, 5 warp-scan steps, block scan,
+    # look-back, carry) = 0.57 ms of multiply-pipe time at 2^24: the IMAD pipe (ncu: 68 % busy), not HBM, is its ceiling
     _, imad = load_measured()
     if imad and imad.get("imad_peak_Tops"):
-        timad = n * 2.5 * 264 / (ms_q * 1e-3) / 1e12
+        timad = n * 2.75 * 264 / (ms_q * 1e-3) / 1e12
         ex["quotient_scan_roofline_imad"] = {"bound": "int32_imad", "achieved": timad, "peak": imad["imad_peak_Tops"],
                                              "unit": "TIMAD/s", "frac": timad / imad["imad_peak_Tops"],
-                                             "note": "2.5 Montgomery multiplies x 264 IMAD per coefficient"}
+                                             "note": "2.75 Montgomery multiplies x 264 IMAD per coefficient"}
+    ms_e = timeit(lambda: ctx.fr_range_eval_dev(sc.data_ptr(), n, u, c0.data_ptr(), q.data_ptr()))
+    ex[f"range_eval_2^{log2n}_ms"] = ms_e  # the reduction form used by the sharded open (writes 64 bytes)
     del sc, q
     if log2n >= 20:
         n = 1 << 20
@@ -711,6 +715,37 @@ def run_extras(ctx, mz, synth, torch, alpha, log2n):
             ctx.commit_batch(rows)
             best = min(best, (time.perf_counter() - t0) * 1e3)
         ex["commit_batch_256_polys_of_2^10_host_api_ms"] = best
+        # MSM over caller-supplied points (accumulate_curve_points call sites): windowed Pippenger without a table
+        m = 1 << 18
+        pts = np.frombuffer(b"".join(mz.context.point_to_bytes(p) for p in ctx.srs_read(0, 4096)), dtype=np.uint8).reshape(-1, 64)
+        pts = np.ascontiguousarray(np.tile(pts, (m // 4096, 1)))
+        scal = synth.random_scalars(m, synth.SEED_SCALARS + 99)
+        import ctypes
+        outp = np.zeros(64, np.uint8)
+        call = lambda: ctx._ck(ctx._lib.myzkp_g1_msm(ctx.h, scal.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p), m,
+                                                     outp.ctypes.data_as(ctypes.c_void_p)))
+        for _ in range(2):
+            call()
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            call()
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        ex["g1_msm_caller_points_2^18_host_api_ms"] = best
+        # verifier latency (three pairings, final exponentiation by parts)
+        g2 = mz.BN128.generator_g2()
+        pk2 = mz.setup_kzg(mz.BN128.generator_g1(), g2, 7, alpha=alpha)
+        f8 = mz.Polynomial(list(range(1, 9)))
+        cm = mz.commit_kzg(f8, pk2)
+        pr = mz.open_kzg(f8, 5, pk2)
+        ok = mz.verify_kzg(5, cm, pr, pk2)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ok = mz.verify_kzg(5, cm, pr, pk2) and ok
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        ex["verify_kzg_ms"] = best
+        ex["verify_kzg_accepts"] = bool(ok)
     return ex
 
 

@@ -62,8 +62,9 @@ uint64_t myzkp_kernel_launches(const myzkp_ctx* ctx);
  * other values fall back to automatic; entries per accumulate segment. */
 int myzkp_ctx_set_msm_params(myzkp_ctx* ctx, int window_bits, int segment_len);
 
-/* Batched-affine rounds in front of the XYZZ bucket accumulate (csrc/baa.cuh):
- * -1 = automatic, 0 = off, r >= 1 = r pairing rounds. */
+/* Bucket-accumulate variant: -1 = automatic (today: the XYZZ mixed-addition kernel), 0 = XYZZ only,
+ * -2 = fused batched-affine pair sums (csrc/msm.cu msm_accumulate_baa; bit-exact, measured slower on
+ * B200 - profiles/baa_r2.md), r >= 1 = r multi-pass batched-affine rounds (csrc/baa.cuh). */
 int myzkp_ctx_set_baa_rounds(myzkp_ctx* ctx, int rounds);
 
 /* Host-buffer commit/open upload a large polynomial in chunks on a copy stream while
@@ -146,8 +147,10 @@ int myzkp_kzg_prove_degree_bound(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t
 /* G1 MSM sum_i scalars[i] * points[i].  points == NULL: against the resident SRS (same as
  * myzkp_kzg_commit).  Otherwise n caller-supplied affine points (the
  * accumulate_curve_points / eval_with_powers_on_curve call sites outside KZG,
- * zksnark/utils.rs:83-93): a temporary table is built for them per call (about 15x the
- * cost of the MSM itself - meant for correctness and moderate sizes, not the hot path). */
+ * zksnark/utils.rs:83-93): classic windowed Pippenger over the points as given - per-window
+ * buckets, then Horner over the windows (~254 dependent doublings, about 1 ms whatever n is).
+ * No table of multiples is built and the resident SRS is neither used nor disturbed; a
+ * coordinate >= p or a scalar >= r is MYZKP_ERR_NONCANONICAL. */
 int myzkp_g1_msm(myzkp_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_or_null /* n*64 */, size_t n,
                  uint8_t out[64]);
 /* G2 MSM sum_i scalars[i] * points[i] with caller-supplied affine G2 points (128 B each, layout as in

@@ -45,7 +45,7 @@ int upload_chunks(const myzkp_ctx* ctx, size_t n) {
   if (ctx->upload_chunks > 0) return (size_t)ctx->upload_chunks <= (n ? n : 1) ? ctx->upload_chunks : 1;
   const char* e = getenv("MZ_UPLOAD_CHUNKS");  // experiment knob
   if (e && atoi(e) > 0) return (size_t)atoi(e) <= (n ? n : 1) ? atoi(e) : 1;
-  if (n >= ((size_t)1 << 24)) return 3;
+  if (n >= ((size_t)1 << 24)) return 4;  // 2^24: 45.2 / 38.5 / 37.2 / 37.0 ms for 1 / 2 / 3 / 4 chunks (resident 35.5)
   if (n >= ((size_t)1 << 21)) return 2;  // measured (scripts/upload_sweep.py): 2^21 6.35 vs 6.93 ms, 2^20 3.90 vs 3.95 ms
   return 1;
 }

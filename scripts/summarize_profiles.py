@@ -40,11 +40,16 @@ def capture(rep, source):
 
 def launch_shares(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit() and r[12] == "gpu__time_duration.sum"]
-    recodes = [i for i, r in enumerate(rows) if "msm_recode" in r[4]]
+    # a commit starts with its recode: msm_recode_count (partitioned recode, round 2) or msm_recode (plain)
+    marker = "msm_recode_count" if any("msm_recode_count" in r[4] for r in rows) else "msm_recode"
+    recodes = [i for i, r in enumerate(rows) if marker in r[4]]
     grid = lambda r: int(r[8].strip("()").split(",")[0])
     big = max(grid(rows[i]) for i in recodes)
     last = max(i for i in recodes if grid(rows[i]) == big)  # the last full-size commit of the run
     nxt = min([i for i in recodes if i > last] + [len(rows)])
+    ends = [i for i in range(last, nxt) if "xyzz_to_affine_bytes" in rows[i][4]]  # a commit ends with its to-affine
+    if ends:
+        nxt = ends[0] + 1
     agg = {}
     for r in rows[last:nxt]:
         name = r[4].split("(")[0].replace("void ", "")
@@ -52,7 +57,7 @@ def launch_shares(path):
         a[0] += 1
         a[1] += float(r[14]) / (1e6 if r[13] in ("ns", "nsecond") else 1e3 if r[13] in ("us", "usecond") else 1.0)
     total = sum(a[1] for a in agg.values())
-    return {"source": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 3 --no-verify "
+    return {"source": "ncu --metrics gpu__time_duration.sum --clock-control none -c 800 python bench.py --steps 2 --warmup 3 --no-verify "
                       "--no-extras (profiles/launches_%s_bench_2p24.csv); the last full-size (2^24) commit of the run; serialised "
                       "cold-cache times - compare SHARES with bench.py's live phases_ms" % ROUND,
             "step_total_ms": round(total, 3),
@@ -60,19 +65,27 @@ def launch_shares(path):
 
 
 if __name__ == "__main__":
-    shutil.copy("gpurun_out/launches_r1_bench.csv", f"profiles/launches_{ROUND}_bench_2p24.csv")
+    if ROUND == "r1":
+        raise SystemExit("round-1 summaries are frozen; run with r2")
+    shutil.copy(f"gpurun_out/launches_{ROUND}_bench_2p24.csv", f"profiles/launches_{ROUND}_bench_2p24.csv")
     json.dump(launch_shares(f"profiles/launches_{ROUND}_bench_2p24.csv"), open(f"profiles/launch_shares_{ROUND}.json", "w"), indent=1)
-    acc = capture("gpurun_out/prof_accumulate_r1.ncu-rep",
-                  "ncu --set full --clock-control none --import-source on -k regex:msm_accumulate (bench.py, 2^24 points, c=22)")
+    acc = capture(f"gpurun_out/prof_accumulate_{ROUND}.ncu-rep",
+                  "ncu --set full --clock-control none --import-source on -k regex:msm_accumulate (scripts/one_commit.py 24, 2^24 points, c=22)")
     json.dump(acc, open(f"profiles/ncu_msm_accumulate_{ROUND}.json", "w"), indent=1)
-    sc = capture("gpurun_out/prof_scatter_r1.ncu-rep",
-                 "ncu --set full --clock-control none --import-source on -k regex:sort_tile_scatter (bench.py, 2^24 points, c=22, "
-                 "201.3M pairs, one of the three passes)")
+    sc = capture(f"gpurun_out/prof_sort_{ROUND}.ncu-rep",
+                 "ncu --set full --clock-control none --import-source on -k regex:sort_tile_scatter|sort_tile_hist|msm_recode "
+                 "(2^24 points, c=22, 201.3M pairs: partitioned recode, then two radix passes inside the partitions)")
     json.dump(sc, open(f"profiles/ncu_sort_{ROUND}.json", "w"), indent=1)
+    rd = capture(f"gpurun_out/prof_reduce_{ROUND}.ncu-rep",
+                 "ncu --set full --clock-control none --import-source on -k regex:msm_bucket_reduce|msm_merge_level|xyzz_tree_reduce (2^24, c=22)")
+    json.dump(rd, open(f"profiles/ncu_merge_reduce_{ROUND}.json", "w"), indent=1)
     a = acc["launches"][0]
     gb = lambda s: float(s.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[s.split()[1]]
     traffic = gb(a["dram__bytes_read.sum"]) + gb(a["dram__bytes_write.sum"])
-    t = json.load(open("profiles/accumulate_traffic_r1.json"))
+    try:
+        t = json.load(open(f"profiles/accumulate_traffic_{ROUND}.json"))
+    except Exception:
+        t = {"source": "dram__bytes_read.sum + dram__bytes_write.sum of msm_accumulate per launch, ncu --set full (scripts/gpu_profiles.sh)"}
     t["2^24_n1"] = traffic
-    json.dump(t, open("profiles/accumulate_traffic_r1.json", "w"), indent=1)
+    json.dump(t, open(f"profiles/accumulate_traffic_{ROUND}.json", "w"), indent=1)
     print("traffic", traffic, "shares total", json.load(open(f"profiles/launch_shares_{ROUND}.json"))["step_total_ms"])

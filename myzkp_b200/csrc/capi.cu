@@ -40,22 +40,29 @@ int begin_call(myzkp_ctx* ctx) {
   return MYZKP_OK;
 }
 
-// Upload pipeline for the host-buffer entry points: how many chunks to split n into
+// Upload pipeline for the host-buffer entry points: how many chunks to split n into.
+// Alone on its host a GPU uploads at ~54 GB/s, a chunk's MSM then takes about four times as long as its upload, and
+// chunk sizes growing 4x expose only the small first upload.  With 4 or more ranks attached (one process per GPU of
+// the same host) the ranks' uploads share the host's memory and PCIe root - measured at 8 ranks: ~23 GB/s each - so
+// an upload takes about half as long as its chunk's MSM and EQUAL chunks expose least.
+bool uploads_contended(const myzkp_ctx* ctx) { return ctx->peer_world >= 4; }
 int upload_chunks(const myzkp_ctx* ctx, size_t n) {
   if (ctx->upload_chunks > 0) return (size_t)ctx->upload_chunks <= (n ? n : 1) ? ctx->upload_chunks : 1;
   const char* e = getenv("MZ_UPLOAD_CHUNKS");  // experiment knob
   if (e && atoi(e) > 0) return (size_t)atoi(e) <= (n ? n : 1) ? atoi(e) : 1;
   if (n >= ((size_t)1 << 24)) return 4;  // 2^24: 45.2 / 38.5 / 37.2 / 37.0 ms for 1 / 2 / 3 / 4 chunks (resident 35.5)
-  if (n >= ((size_t)1 << 21)) return 2;  // measured (scripts/upload_sweep.py): 2^21 6.35 vs 6.93 ms, 2^20 3.90 vs 3.95 ms
+  if (n >= ((size_t)1 << 21)) return uploads_contended(ctx) ? 4 : 2;  // 2^21 alone: 6.75 / 6.04 / 6.25 / 6.52 ms (resident 5.51)
   return 1;
 }
-// Chunk `pos` (in processing order) of n coefficients cut into K chunks whose sizes grow 4x: the
-// MSM of a chunk takes about four times as long as its upload, so a chunk four times larger can be
-// uploaded meanwhile and only the small first upload is exposed.  Descending: the first chunk
-// processed is the top of the polynomial (the quotient scan runs downwards).
-void chunk_range(size_t n, int K, int pos, bool descending, size_t* lo, size_t* hi) {
-  const unsigned __int128 total = (((unsigned __int128)1 << (2 * K)) - 1);
-  auto cum = [&](int p) { return (size_t)(((unsigned __int128)n * ((((unsigned __int128)1) << (2 * p)) - 1)) / total); };
+// Chunk `pos` (in processing order) of n coefficients cut into K chunks whose sizes grow by `ratio` (4, or 1 = equal
+// chunks).  Descending: the first chunk processed is the top of the polynomial (the quotient scan runs downwards).
+void chunk_range(const myzkp_ctx* ctx, size_t n, int K, int pos, bool descending, size_t* lo, size_t* hi) {
+  const bool equal = uploads_contended(ctx) || getenv("MZ_UPLOAD_EQUAL");
+  const unsigned __int128 total = equal ? (unsigned __int128)K : (((unsigned __int128)1 << (2 * K)) - 1);
+  auto cum = [&](int p) {
+    const unsigned __int128 w = equal ? (unsigned __int128)p : ((((unsigned __int128)1) << (2 * p)) - 1);
+    return (size_t)(((unsigned __int128)n * w) / total);
+  };
   size_t a = cum(pos), b = pos + 1 == K ? n : cum(pos + 1);
   if (descending) {
     *lo = n - b;
@@ -80,7 +87,7 @@ int enqueue_chunk_uploads(myzkp_ctx* ctx, const uint8_t* host, uint8_t* dev, siz
   MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done_ev, 0));
   for (int pos = 0; pos < K; pos++) {
     size_t lo, hi;
-    chunk_range(n, K, pos, descending, &lo, &hi);
+    chunk_range(ctx, n, K, pos, descending, &lo, &hi);
     if (lo < hi)
       MZ_CUDA_TRY(ctx, cudaMemcpyAsync(dev + lo * 32, host + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
     MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[pos], ctx->copy_stream));
@@ -155,7 +162,7 @@ int chunked_msm(myzkp_ctx* ctx, uint32_t* d_coefs, size_t n, int K, bool descend
   bool first = true;
   for (int pos = 0; pos < K; pos++) {
     size_t lo, hi;
-    chunk_range(n, K, pos, descending, &lo, &hi);
+    chunk_range(ctx, n, K, pos, descending, &lo, &hi);
     MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[pos], 0));
     if (lo >= hi) continue;
     const uint32_t* sc = d_coefs + lo * 8;

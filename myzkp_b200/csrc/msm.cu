@@ -776,6 +776,12 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
 // the supported window with the least work - 10 multiplies per entry (W(c) entries per coefficient)
 // against 2 x 14 multiplies per bucket (2^(c-1) buckets per polynomial) - within a 2 GiB bucket budget.
 int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K) {
+  {  // a forced window (myzkp_ctx_set_msm_params) applies to batches too, when the bucket sets fit
+    const int forced = ctx->window_bits;
+    if (forced >= 1 && forced <= 24 && ((ctx->windows >> forced) & 1) && ((uint64_t)K << (forced - 1)) < (1ull << 32) - 1 &&
+        ((uint64_t)K << (forced - 1)) * sizeof(XYZZ) <= (8ull << 30))
+      return forced;
+  }
   uint64_t total = 0;
   for (size_t y = 0; y < K; y++) total += items[y].n;
   int best = 0;

@@ -366,6 +366,23 @@ def test_commit_batch_one_pipeline(ctx):
         ctx.commit_batch([polys[5], bad])
 
 
+def test_commit_batch_with_partitioned_sort(ctx):
+    """A batch whose bucket keys are wider than 16 bits takes the MSD-partitioned recode with per-polynomial bucket
+    ranges (msm_recode_count / msm_recode_scatter with descriptors, csrc/msm.cu): forced windows 20, 22 and 24 on a
+    small batch, ragged lengths, an empty and an all-zero polynomial."""
+    rnd = random.Random(33)
+    alpha = 0x1234567
+    ctx.srs_generate(alpha, 3000)
+    polys = [[rnd.randrange(R) for _ in range(n)] for n in (3000, 1, 517, 2048)] + [[], [0] * 40, [rnd.randrange(256) for _ in range(999)]]
+    exp = [o.expected_commit(p_, alpha) for p_ in polys]
+    try:
+        for c in (20, 22, 24, 16):
+            ctx.set_msm_params(c, 0)
+            assert ctx.commit_batch(polys) == exp, c
+    finally:
+        ctx.set_msm_params(0, 0)
+
+
 def test_commit_batch_mixed_large_and_small(ctx):
     """A batch with one polynomial above the own-MSM threshold (2^19) next to small ones: results come
     back in caller order."""

@@ -227,12 +227,10 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   const uint32_t wbase = (uint32_t)w * (32 * kSortItems);
 
   const uint32_t ntiles = parts ? parts[2 * P + 1] : ntiles_arg;  // tile_start[P]
-  // where a tile lives (partition, offset, histogram slot) is looked up by ONE thread, two tiles ahead, and
-  // handed over through shared memory: the binary search over the partition table does not run in every thread
-  __shared__ TileRef s_ref[2];
   uint32_t k[kSortItems], v[kSortItems], kn[kSortItems], vn[kSortItems], rank[kSortItems];
   uint32_t gb = 0, gbn = 0, tn_next = 0;
-  auto fetch = [&](const TileRef& ref, uint32_t* kk, uint32_t* vv, uint32_t& g) {
+  auto fetch = [&](uint32_t tile, uint32_t* kk, uint32_t* vv, uint32_t& g) {
+    const TileRef ref = locate_tile(tile, parts, P, n, ntiles);
     const uint64_t tb = ref.base;
     const uint32_t tn = ref.count;
     tn_next = tn;
@@ -249,25 +247,17 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     g = hist_scanned[ref.hist_base + (size_t)threadIdx.x * ref.hist_stride];
   };
   uint32_t tile = blockIdx.x;
-  if (threadIdx.x == 0) {
-    s_ref[0] = locate_tile(tile, parts, P, n, ntiles);
-    s_ref[1] = locate_tile(tile + gridDim.x, parts, P, n, ntiles);
-  }
-  __syncthreads();
-  if (tile < ntiles) fetch(s_ref[0], kn, vn, gbn);
-  for (int par = 0; tile < ntiles; tile += gridDim.x, par ^= 1) {
+  if (tile < ntiles) fetch(tile, kn, vn, gbn);
+  for (; tile < ntiles; tile += gridDim.x) {
     const uint32_t tile_n = tn_next;
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) { k[i] = kn[i]; v[i] = vn[i]; }
     gb = gbn;
-    if (tile + gridDim.x < ntiles) fetch(s_ref[par ^ 1], kn, vn, gbn);  // in flight during the ranking below
+    if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x, kn, vn, gbn);  // in flight during the ranking below
 #pragma unroll
     for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
     gbase[threadIdx.x] = gb;
     __syncthreads();
-    // every thread has read s_ref[par ^ 1] (fetch above) and s_ref[par] one iteration ago: refill s_ref[par] for the
-    // tile after next; the barriers below publish it before it is read at the top of the next-but-one iteration
-    if (threadIdx.x == 0) s_ref[par] = locate_tile(tile + 2 * gridDim.x, parts, P, n, ntiles);
     if (kStable) {
       // all 16 matches first (they only depend on the keys, so they pipeline), then the
       // sequential per-warp counter updates

@@ -95,6 +95,27 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: run this rank's host thread (and so place its pinned upload buffer, first touched by this
+    thread) on the CPUs NVML reports as local to the GPU, so that the ranks' concurrent H2D copies do not all cross the
+    socket interconnect.  Host placement only; returns the CPU count bound to, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------
 # reference arm: the oracle port (C restatement of the reference's naive algorithm) on the host
 # --------------------------------------------------------------------------------------
@@ -196,6 +217,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - myzkp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -434,7 +456,7 @@ def main():
                               "note": "resident table of 2^(b_j) multiples of every SRS point (the design's price for an MSM "
                                       "without doublings): rows x 64 B per point; myzkp_ctx_set_table_windows restricts it "
                                       "(window 22 alone = 12 rows)"},
-                "window_bits": info.get("window_bits"), "srs_setup_s": t_srs,
+                "window_bits": info.get("window_bits"), "srs_setup_s": t_srs, "host_cpus_bound_to_gpu_numa_node": numa,
             },
             "commits_per_sec": 1e3 / ms_step,
             "e2e": {"value": e2e_val, "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n_total * 32,

@@ -663,33 +663,42 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
       len /= 2;
     }
   }
-  // ... then the commitments.  Levels of >= 2^19 coefficients get their own MSM on this stream; all
-  // smaller levels (2^19 - 1 coefficients together) run as ONE batched pipeline on a child context
-  // (own stream and scratch, same SRS table), concurrently with the large ones.
+  // ... then the commitments.  Levels of >= 2^20 coefficients get their own MSM on this stream; the levels below run
+  // as TWO batched pipelines on child contexts (own stream and scratch, same SRS table), concurrently with the large
+  // ones: 2^16 .. 2^19 coefficients together (window 16 by the batch cost model) and everything below 2^16 (window 12).
+  // One batch for all small levels would force one window on them: the bucket reduce of 2^15 buckets per polynomial
+  // costs more than the commitments of the tiny levels themselves (round 1: 8.5 ms for 2^20, of which ~1 ms was that).
   if (!ctx->fork_ev) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  std::vector<MsmItem> small_levels;
-  int first_small = m + 1;
+  constexpr size_t kGemOwn = (size_t)1 << 20, kGemMid = (size_t)1 << 16;
+  std::vector<MsmItem> cls[2];  // 0: mid batch, 1: small batch
+  int first_of[2] = {m + 1, m + 1};
+  int first_small = m + 1;      // first level that is not an own-stream MSM
   {
     uint32_t* cur = base;
     size_t len = n_pow2;
     for (int lvl = 0; lvl <= m; lvl++) {
-      if (len < kBatchBelow) {
-        if (small_levels.empty()) first_small = lvl;
-        small_levels.push_back(MsmItem{cur, len});
+      if (len < kGemOwn) {
+        const int k = len >= kGemMid ? 0 : 1;
+        if (cls[k].empty()) first_of[k] = lvl;
+        if (first_small > lvl) first_small = lvl;
+        cls[k].push_back(MsmItem{cur, len});
       }
       cur += len * 8;
       len /= 2;
     }
   }
-  myzkp_ctx* ch = nullptr;
+  myzkp_ctx* chs[2] = {nullptr, nullptr};
   int rc_child = MYZKP_OK, rc_parent = MYZKP_OK;
-  bool child_launched = false;
-  if (!small_levels.empty()) {
-    MZ_TRY(get_child(ctx, 0, &ch));
+  const char* child_err = "";
+  for (int k = 0; k < 2 && rc_child == MYZKP_OK; k++) {
+    if (cls[k].empty()) continue;
+    myzkp_ctx* ch = nullptr;
+    MZ_TRY(get_child(ctx, k, &ch));
     MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, ctx->fork_ev, 0));  // the folds come first
-    child_launched = true;
-    rc_child = msm_batch_xyzz(ch, small_levels.data(), small_levels.size(), 0, res + first_small);
+    chs[k] = ch;
+    rc_child = msm_batch_xyzz(ch, cls[k].data(), cls[k].size(), 0, res + first_of[k]);
+    if (rc_child != MYZKP_OK) child_err = ch->err.c_str();
     ctx->launches += ch->launches;
     ch->launches = 0;
   }
@@ -702,9 +711,11 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
       len /= 2;
     }
   }
-  // join: whatever was enqueued on the child reads `base` and writes `res`, so the parent stream waits for it on
+  // join: whatever was enqueued on a child reads `base` and writes `res`, so the parent stream waits for it on
   // every path out of here, error paths included
-  if (child_launched) {
+  for (int k = 0; k < 2; k++) {
+    myzkp_ctx* ch = chs[k];
+    if (!ch) continue;
     cudaError_t je = cudaEventRecord(ch->join_ev, ch->stream);
     if (je == cudaSuccess) je = cudaStreamWaitEvent(ctx->stream, ch->join_ev, 0);
     if (je != cudaSuccess) {
@@ -712,7 +723,7 @@ int myzkp_gemini_fold_commit(myzkp_ctx* ctx, const uint8_t* coefs_le, size_t n_p
       cudaGetLastError();
     }
   }
-  if (rc_child != MYZKP_OK) return fail(ctx, rc_child, ch->err.c_str());
+  if (rc_child != MYZKP_OK) return fail(ctx, rc_child, child_err);
   if (rc_parent != MYZKP_OK) return rc_parent;
   MZ_TRY(xyzz_to_bytes(ctx, res, (size_t)(m + 1), d_pts));
   MZ_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_pts, (size_t)(m + 1) * 64, cudaMemcpyDeviceToHost, ctx->stream));

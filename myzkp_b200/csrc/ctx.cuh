@@ -96,7 +96,7 @@ struct myzkp_ctx {
   mz::DevBuf heads2;       // ping-pong levels of the head merge
   mz::DevBuf baa_pts, baa_keys, baa_prefix, baa_meta, baa_trans;  // batched-affine rounds: private lists, prefixes, products
   int baa_rounds = -1;     // -1 = automatic, 0 = off (XYZZ accumulate only)
-  mz::DevBuf red_a, red_b; // reduction partials (XYZZ)
+  mz::DevBuf red_a, red_b, red_c; // reduction partials (XYZZ)
   mz::DevBuf poly_tiles;   // per-tile (mult, add) maps for the quotient scan
   mz::DevBuf small;        // misc small device outputs (flags, y, points)
   bool small_init = false; // the sticky non-canonical flag inside `small` has been zeroed once
@@ -139,7 +139,7 @@ inline void for_each_scratch(myzkp_ctx* ctx, F f) {
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                     &ctx->sort_tmp, &ctx->sort_parts, &ctx->caller_points, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
                     &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
-                    &ctx->red_a, &ctx->red_b, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
+                    &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
   for (DevBuf* b : bufs) f(b);
 }
 }  // namespace mz

@@ -625,18 +625,47 @@ __global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ bucket
 // ---------------------------------------------------------------------------
 // 5. bucket reduce: sum_{idx} (idx + 1) * B[idx]
 // ---------------------------------------------------------------------------
-// thread j owns buckets [j*Lb, (j+1)*Lb): running sums give A = sum B and
-// S = sum (idx - j*Lb + 1) B; its contribution is S + (j*Lb) * A.
-// blockIdx.y = bucket set of a batch (sets of nb buckets back to back; out: nchunks partials per set)
-__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ buckets_all, uint32_t nb, uint32_t Lb,
-                                                         XYZZ* __restrict__ out_all, uint32_t nchunks) {
+// Two levels.  Level 1 (msm_bucket_chunks): thread j owns buckets [j*Lb, (j+1)*Lb); running sums give
+// A_j = sum B and S_j = sum (idx - j*Lb + 1) B.  The whole sum is sum_j S_j + Lb * sum_j j A_j, and the second
+// term is the same problem over the n1 = nb / Lb values A_j: level 2 (msm_bucket_reduce on A_1 ..) solves it with
+// longer chunks and pays the offset of a chunk with a double-and-add by the (small, public) chunk start; Lb is a
+// power of two, so the factor Lb is `shift` doublings of each level-2 partial.  Level 1 therefore runs 2 additions
+// per bucket and nothing else (round 1 ran the double-and-add in every level-1 thread: +22 % at c = 22, +100 % at
+// c = 20, and could not use more than two warps per sub-partition because of it).
+// blockIdx.y = bucket set of a batch (sets of nb buckets back to back)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks)
+    msm_bucket_chunks(const XYZZ* __restrict__ buckets_all, uint32_t nb, uint32_t Lb, XYZZ* __restrict__ out_s_all,
+                      uint64_t s_stride, XYZZ* __restrict__ out_a_all, uint32_t n1) {
   const XYZZ* __restrict__ buckets = buckets_all + (size_t)blockIdx.y * nb;
-  XYZZ* __restrict__ out = out_all + (size_t)blockIdx.y * nchunks;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n1) return;
   uint64_t lo = (uint64_t)j * Lb;
-  if (lo >= nb) return;
   uint64_t hi = lo + Lb < nb ? lo + Lb : nb;
   XYZZ run = xyzz_inf(), sum = xyzz_inf();
+#pragma unroll 1
+  for (uint64_t idx = hi; idx > lo; idx--) {
+    XYZZ b = load_xyzz(buckets + (idx - 1));
+    xyzz_add(run, b);
+    xyzz_add(sum, run);
+  }
+  store_xyzz(out_s_all + (size_t)blockIdx.y * s_stride + j, sum);
+  store_xyzz(out_a_all + (size_t)blockIdx.y * n1 + j, run);
+}
+
+// thread j owns values [j*Lb, (j+1)*Lb) of its set: S = sum (idx - j*Lb + 1) V plus (j*Lb) * sum V by
+// double-and-add, then 2^shift * that.  Set y starts at in_all + y * in_stride and holds nb values.
+__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ in_all, uint64_t in_stride, uint32_t nb,
+                                                         uint32_t Lb, int shift, XYZZ* __restrict__ out_all,
+                                                         uint64_t out_stride, uint32_t nchunks) {
+  const XYZZ* __restrict__ buckets = in_all + (size_t)blockIdx.y * in_stride;
+  XYZZ* __restrict__ out = out_all + (size_t)blockIdx.y * out_stride;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nchunks) return;
+  uint64_t lo = (uint64_t)j * Lb;
+  uint64_t hi = lo + Lb < nb ? lo + Lb : nb;
+  XYZZ run = xyzz_inf(), sum = xyzz_inf();
+#pragma unroll 1
   for (uint64_t idx = hi; idx > lo; idx--) {
     XYZZ b = load_xyzz(buckets + (idx - 1));
     xyzz_add(run, b);
@@ -646,12 +675,15 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict_
   if (lo != 0 && !xyzz_is_inf(run)) {
     XYZZ m = xyzz_inf();
     int top = 63 - __clzll((unsigned long long)lo);
+#pragma unroll 1
     for (int bit = top; bit >= 0; bit--) {
       xyzz_dbl(m);
       if ((lo >> bit) & 1) xyzz_add(m, run);
     }
     xyzz_add(sum, m);
   }
+#pragma unroll 1
+  for (int k = 0; k < shift; k++) xyzz_dbl(sum);
   store_xyzz(out + j, sum);
 }
 
@@ -1014,21 +1046,54 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
   const uint32_t nb = 1u << (c - 1);
   const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
   const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
-  // chunk length, from a sweep on B200 (profiles/experiments_r1.md): two blocks of 128 threads per SM
-  // (more warps per sub-partition made the kernel slower, fewer left SMs idle), at least 4 buckets
-  // per thread (each thread also pays a ~30-operation double-and-add by its chunk offset)
-  const uint64_t target = (uint64_t)ctx->sm_count * 2 * 128;
-  uint32_t Lb = (uint32_t)(((uint64_t)nb * K + target - 1) / target);
-  if (Lb < 4) Lb = 4;
-  if (Lb > 256) Lb = 256;
+  // Level 1: chunks of Lb buckets (a power of two), about kL1PerSm threads per SM over the whole batch - the kernel is
+  // two additions per bucket and nothing else, so more resident warps only help until the multiply pipe is full.
+  static const int env_lb = getenv("MZ_REDUCE_LB") ? atoi(getenv("MZ_REDUCE_LB")) : 0;        // experiment knobs
+  static const int env_lb2 = getenv("MZ_REDUCE_LB2") ? atoi(getenv("MZ_REDUCE_LB2")) : 0;
+  static const int env_minb = getenv("MZ_REDUCE_MINB") ? atoi(getenv("MZ_REDUCE_MINB")) : 3;
+  constexpr uint64_t kL1PerSm = 256;
+  uint32_t Lb = 1;
+  while ((uint64_t)nb * K / (2 * Lb) >= (uint64_t)ctx->sm_count * kL1PerSm && Lb < 64) Lb *= 2;
+  if (env_lb > 0) Lb = (uint32_t)env_lb;
   if (Lb > nb) Lb = nb;
-  uint32_t nchunks = (nb + Lb - 1) / Lb;
-  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)K * nchunks * sizeof(XYZZ)));
-  MZ_CUDA_TRY(ctx, ctx->red_b.ensure((size_t)K * ((size_t)nchunks / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
-  msm_bucket_reduce<<<dim3((nchunks + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(buckets, nb, Lb,
-                                                                                      ctx->red_a.as<XYZZ>(), nchunks);
+  if (Lb < 8) Lb = 1;  // small bucket sets: one level (the second level's latency would exceed what the first saves)
+  int shift = 0;
+  while ((1u << shift) < Lb) shift++;
+  if ((1u << shift) != Lb) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bucket reduce: chunk length must be a power of two");
+  const uint32_t n1 = Lb > 1 ? nb / Lb : 0;  // nb is a power of two too
+  // Level 2 over A_1 .. A_{n1-1} (A_0 has weight 0) - or the only level, over the buckets themselves: two blocks of
+  // 128 threads per SM, at least 4 values per thread (each thread also pays a ~30-operation double-and-add by its
+  // chunk offset; sweep in profiles/experiments_r1.md)
+  const uint32_t nb2 = n1 ? n1 - 1 : nb;
+  const uint64_t target = (uint64_t)ctx->sm_count * 2 * 128;
+  uint32_t Lb2 = (uint32_t)(((uint64_t)nb2 * K + target - 1) / target);
+  if (Lb2 < 4) Lb2 = 4;
+  if (Lb2 > 256) Lb2 = 256;
+  if (env_lb2 > 0) Lb2 = (uint32_t)env_lb2;
+  if (Lb2 > nb2) Lb2 = nb2;
+  const uint32_t n2 = (nb2 + Lb2 - 1) / Lb2;
+  const uint64_t per_set = (uint64_t)n1 + n2;  // values the tree sums per set: S_0 .. S_{n1-1}, then the level-2 partials
+  MZ_CUDA_TRY(ctx, ctx->red_a.ensure((size_t)K * per_set * sizeof(XYZZ)));
+  MZ_CUDA_TRY(ctx, ctx->red_b.ensure((size_t)K * ((size_t)per_set / (2 * kTreeThreads) + 2) * sizeof(XYZZ)));
+  XYZZ* d_s = ctx->red_a.as<XYZZ>();
+  if (n1) {
+    MZ_CUDA_TRY(ctx, ctx->red_c.ensure((size_t)K * n1 * sizeof(XYZZ)));
+    XYZZ* d_a = ctx->red_c.as<XYZZ>();
+    const dim3 g1((n1 + 127) / 128, (unsigned)K);
+    if (env_minb >= 4)
+      msm_bucket_chunks<4><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
+    else if (env_minb == 3)
+      msm_bucket_chunks<3><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
+    else
+      msm_bucket_chunks<2><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
+    MZ_LAUNCH_CHECK(ctx);
+    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(d_a + 1, n1, nb2, Lb2, shift, d_s + n1,
+                                                                                  per_set, n2);
+  } else {
+    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(buckets, nb, nb, Lb2, 0, d_s, per_set, n2);
+  }
   MZ_LAUNCH_CHECK(ctx);
-  MZ_TRY(tree_sum(ctx, ctx->red_a.as<XYZZ>(), ctx->red_b.as<XYZZ>(), nchunks, d_out, (uint32_t)K));
+  MZ_TRY(tree_sum(ctx, d_s, ctx->red_b.as<XYZZ>(), per_set, d_out, (uint32_t)K));
   if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][5], ctx->stream));
   ctx->phase_valid[slot] = timing;
   ctx->phase_pending = false;

@@ -628,10 +628,46 @@ __global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ bucket
 // Two levels.  Level 1 (msm_bucket_chunks): thread j owns buckets [j*Lb, (j+1)*Lb); running sums give
 // A_j = sum B and S_j = sum (idx - j*Lb + 1) B.  The whole sum is sum_j S_j + Lb * sum_j j A_j, and the second
 // term is the same problem over the n1 = nb / Lb values A_j: level 2 (msm_bucket_reduce on A_1 ..) solves it with
-// longer chunks and pays the offset of a chunk with a double-and-add by the (small, public) chunk start; Lb is a
-// power of two, so the factor Lb is `shift` doublings of each level-2 partial.  Level 1 therefore runs 2 additions
+// short chunks and pays the offset of a chunk with a double-and-add by the (small, public) chunk start; the factor Lb
+// is one more small double-and-add on each level-2 partial.  Level 1 therefore runs 2 additions
 // per bucket and nothing else (round 1 ran the double-and-add in every level-1 thread: +22 % at c = 22, +100 % at
 // c = 20, and could not use more than two warps per sub-partition because of it).
+// run = sum B, sum = sum (idx - lo + 1) B over [lo, hi), walking down from hi.  ONE instance of the general addition
+// in the loop: a step either adds the next bucket to `run` or `run` to `sum`, operands picked by selects - two inlined
+// additions (~33 KB of SASS each) do not fit the 32 KB instruction cache, and the kernel then waits on instruction
+// fetches instead of the multiply pipe.
+__device__ __forceinline__ XYZZ xyzz_select(bool c, const XYZZ& a, const XYZZ& b) {
+  XYZZ r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.v[i] = c ? a.x.v[i] : b.x.v[i];
+    r.y.v[i] = c ? a.y.v[i] : b.y.v[i];
+    r.zz.v[i] = c ? a.zz.v[i] : b.zz.v[i];
+    r.zzz.v[i] = c ? a.zzz.v[i] : b.zzz.v[i];
+  }
+  return r;
+}
+__device__ __forceinline__ void running_sums(const XYZZ* __restrict__ buckets, uint64_t lo, uint64_t hi, XYZZ& run, XYZZ& sum) {
+  if (hi <= lo) return;
+  uint64_t idx = hi;
+  XYZZ q = load_xyzz(buckets + (idx - 1));
+  bool to_run = true;
+#pragma unroll 1
+  while (true) {
+    XYZZ acc = xyzz_select(to_run, run, sum);
+    xyzz_add(acc, q);
+    if (to_run) {
+      run = acc;
+      q = acc;  // next step: sum += run
+    } else {
+      sum = acc;
+      if (--idx == lo) break;
+      q = load_xyzz(buckets + (idx - 1));
+    }
+    to_run = !to_run;
+  }
+}
+
 // blockIdx.y = bucket set of a batch (sets of nb buckets back to back)
 template <int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks)
@@ -643,20 +679,15 @@ __global__ void __launch_bounds__(128, kMinBlocks)
   uint64_t lo = (uint64_t)j * Lb;
   uint64_t hi = lo + Lb < nb ? lo + Lb : nb;
   XYZZ run = xyzz_inf(), sum = xyzz_inf();
-#pragma unroll 1
-  for (uint64_t idx = hi; idx > lo; idx--) {
-    XYZZ b = load_xyzz(buckets + (idx - 1));
-    xyzz_add(run, b);
-    xyzz_add(sum, run);
-  }
+  running_sums(buckets, lo, hi, run, sum);
   store_xyzz(out_s_all + (size_t)blockIdx.y * s_stride + j, sum);
   store_xyzz(out_a_all + (size_t)blockIdx.y * n1 + j, run);
 }
 
 // thread j owns values [j*Lb, (j+1)*Lb) of its set: S = sum (idx - j*Lb + 1) V plus (j*Lb) * sum V by
-// double-and-add, then 2^shift * that.  Set y starts at in_all + y * in_stride and holds nb values.
+// double-and-add, then scale * that.  Set y starts at in_all + y * in_stride and holds nb values.
 __global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict__ in_all, uint64_t in_stride, uint32_t nb,
-                                                         uint32_t Lb, int shift, XYZZ* __restrict__ out_all,
+                                                         uint32_t Lb, int scale, XYZZ* __restrict__ out_all,
                                                          uint64_t out_stride, uint32_t nchunks) {
   const XYZZ* __restrict__ buckets = in_all + (size_t)blockIdx.y * in_stride;
   XYZZ* __restrict__ out = out_all + (size_t)blockIdx.y * out_stride;
@@ -665,12 +696,7 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict_
   uint64_t lo = (uint64_t)j * Lb;
   uint64_t hi = lo + Lb < nb ? lo + Lb : nb;
   XYZZ run = xyzz_inf(), sum = xyzz_inf();
-#pragma unroll 1
-  for (uint64_t idx = hi; idx > lo; idx--) {
-    XYZZ b = load_xyzz(buckets + (idx - 1));
-    xyzz_add(run, b);
-    xyzz_add(sum, run);
-  }
+  running_sums(buckets, lo, hi, run, sum);
   // sum += lo * run  (MSB-first double-and-add on the small public scalar lo)
   if (lo != 0 && !xyzz_is_inf(run)) {
     XYZZ m = xyzz_inf();
@@ -682,8 +708,16 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ* __restrict_
     }
     xyzz_add(sum, m);
   }
+  // sum *= scale (the level-1 chunk length, a small public constant)
+  if (scale > 1 && !xyzz_is_inf(sum)) {
+    XYZZ m = sum;
 #pragma unroll 1
-  for (int k = 0; k < shift; k++) xyzz_dbl(sum);
+    for (int bit = 30 - __clz(scale); bit >= 0; bit--) {
+      xyzz_dbl(m);
+      if ((scale >> bit) & 1) xyzz_add(m, sum);
+    }
+    sum = m;
+  }
   store_xyzz(out + j, sum);
 }
 
@@ -1046,21 +1080,19 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
   const uint32_t nb = 1u << (c - 1);
   const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
   const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
-  // Level 1: chunks of Lb buckets (a power of two), about kL1PerSm threads per SM over the whole batch - the kernel is
-  // two additions per bucket and nothing else, so more resident warps only help until the multiply pipe is full.
+  // Level 1: chunks of Lb buckets - the kernel is two additions per bucket and nothing else.
   static const int env_lb = getenv("MZ_REDUCE_LB") ? atoi(getenv("MZ_REDUCE_LB")) : 0;        // experiment knobs
   static const int env_lb2 = getenv("MZ_REDUCE_LB2") ? atoi(getenv("MZ_REDUCE_LB2")) : 0;
-  static const int env_minb = getenv("MZ_REDUCE_MINB") ? atoi(getenv("MZ_REDUCE_MINB")) : 3;
-  constexpr uint64_t kL1PerSm = 256;
-  uint32_t Lb = 1;
-  while ((uint64_t)nb * K / (2 * Lb) >= (uint64_t)ctx->sm_count * kL1PerSm && Lb < 64) Lb *= 2;
+  static const int env_minb = getenv("MZ_REDUCE_MINB") ? atoi(getenv("MZ_REDUCE_MINB")) : 2;
+  // exactly one wave of level-1 threads (kReduceMinBlocks blocks of 128 per SM): a power-of-two chunk length left a
+  // second wave 15 % full at c = 22 (ncu, profiles/experiments_r2.md)
+  const int minb = env_minb >= 4 ? 4 : env_minb == 3 ? 3 : 2;
+  const uint64_t wave = (uint64_t)ctx->sm_count * minb * 128;
+  uint32_t Lb = (uint32_t)(((uint64_t)nb * K + wave - 1) / wave);
   if (env_lb > 0) Lb = (uint32_t)env_lb;
   if (Lb > nb) Lb = nb;
   if (Lb < 8) Lb = 1;  // small bucket sets: one level (the second level's latency would exceed what the first saves)
-  int shift = 0;
-  while ((1u << shift) < Lb) shift++;
-  if ((1u << shift) != Lb) return fail(ctx, MYZKP_ERR_INVALID_ARG, "bucket reduce: chunk length must be a power of two");
-  const uint32_t n1 = Lb > 1 ? nb / Lb : 0;  // nb is a power of two too
+  const uint32_t n1 = Lb > 1 ? (nb + Lb - 1) / Lb : 0;
   // Level 2 over A_1 .. A_{n1-1} (A_0 has weight 0) - or the only level, over the buckets themselves: two blocks of
   // 128 threads per SM, at least 4 values per thread (each thread also pays a ~30-operation double-and-add by its
   // chunk offset; sweep in profiles/experiments_r1.md)
@@ -1080,17 +1112,17 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
     MZ_CUDA_TRY(ctx, ctx->red_c.ensure((size_t)K * n1 * sizeof(XYZZ)));
     XYZZ* d_a = ctx->red_c.as<XYZZ>();
     const dim3 g1((n1 + 127) / 128, (unsigned)K);
-    if (env_minb >= 4)
+    if (minb == 4)
       msm_bucket_chunks<4><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
-    else if (env_minb == 3)
+    else if (minb == 3)
       msm_bucket_chunks<3><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
     else
       msm_bucket_chunks<2><<<g1, 128, 0, ctx->stream>>>(buckets, nb, Lb, d_s, per_set, d_a, n1);
     MZ_LAUNCH_CHECK(ctx);
-    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(d_a + 1, n1, nb2, Lb2, shift, d_s + n1,
+    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(d_a + 1, n1, nb2, Lb2, (int)Lb, d_s + n1,
                                                                                   per_set, n2);
   } else {
-    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(buckets, nb, nb, Lb2, 0, d_s, per_set, n2);
+    msm_bucket_reduce<<<dim3((n2 + 127) / 128, (unsigned)K), 128, 0, ctx->stream>>>(buckets, nb, nb, Lb2, 1, d_s, per_set, n2);
   }
   MZ_LAUNCH_CHECK(ctx);
   MZ_TRY(tree_sum(ctx, d_s, ctx->red_b.as<XYZZ>(), per_set, d_out, (uint32_t)K));

@@ -39,7 +39,8 @@ for item in spec:
             torch.cuda.synchronize()
             ph, info = ctx.msm_phases(0)
             row = {"log2n": lg, "c": info["window_bits"], "L": info["segment_len"], "segs": info["segments"],
-                   "total_ms": round(e0.elapsed_time(e1) / reps, 3), **{k: round(v, 3) for k, v in ph.items()}}
+                   "total_ms": round(e0.elapsed_time(e1) / reps, 3), **{k: round(v, 3) for k, v in ph.items()},
+                   "out": bytes(out.cpu().numpy())[:8].hex()}
             res.append(row)
             print(json.dumps(row), flush=True)
 json.dump(res, open("gpurun_out/phase_sweep.json", "w"), indent=1)

@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=512, help="--impl reference: coefficients per step (1 core, ~3.4 ms each)")
     ap.add_argument("--no-verify", action="store_true", help="skip the O(N) host check of the full-size commitment")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="development: only the headline commit (no open / C3 / C5 timings)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory exchange kernel (default) or NCCL all_gather + sum")
     ap.add_argument("--window-bits", type=int, default=0)
@@ -413,7 +414,8 @@ def main():
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "phase_ms": sort_ms}
 
     # ---- the other BASELINE configs at this N: open at 2^24, C3 (2^20 commit + open), C5 (Gemini) ---------------
-    configs = run_configs(args, mz, synth, torch, dist, ctx, ops, prover, d_scal, scal_all, alpha, rank, world, dev, barrier)
+    configs = None if args.skip_configs else run_configs(args, mz, synth, torch, dist, ctx, ops, prover, d_scal, scal_all, alpha,
+                                                          rank, world, dev, barrier)
 
     # ---- cpu baseline + extras (rank 0, N = 1) -----------------------------------------------
     cpu_baseline = None

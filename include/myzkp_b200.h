@@ -261,6 +261,9 @@ int myzkp_test_field_op(myzkp_ctx* ctx, int field, int op, const uint8_t* a, con
  * integer in the first 32 bytes of b[i] (double-and-add in XYZZ), 3 a[i]+b[i]
  * through XYZZ+XYZZ with non-trivial denominators.  Points are 64 B affine. */
 int myzkp_test_g1_op(myzkp_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* Entries a group may hold for the shared-memory group sort of the MSM's bucket sort (0 = default, 13312).  Tests
+ * lower it so that small inputs reach the path skewed scalars take at full size (oversize groups).  Process-wide. */
+int myzkp_test_set_sort_group_cap(int cap);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ SIGNATURES = {
     "myzkp_fr_range_quotient_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "myzkp_test_field_op": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "myzkp_test_g1_op": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "myzkp_test_set_sort_group_cap": (_i, [_i]),
 }
 
 _lib = None

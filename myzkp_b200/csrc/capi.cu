@@ -1,6 +1,7 @@
 // extern "C" entry points of libmyzkp_b200.so (see include/myzkp_b200.h).
 #include <string.h>
 
+#include <cmath>
 #include <vector>
 
 #include "ctx.cuh"
@@ -56,14 +57,17 @@ int upload_chunks(const myzkp_ctx* ctx, size_t n) {
 }
 // Chunk `pos` (in processing order) of n coefficients cut into K chunks whose sizes grow by `ratio` (4, or 1 = equal
 // chunks).  Descending: the first chunk processed is the top of the polynomial (the quotient scan runs downwards).
+// growth ratio of the upload chunks: 4 alone on the host, kContendedRatio when the ranks' uploads share it
+constexpr double kContendedRatio = 1.0;
+double upload_ratio(const myzkp_ctx* ctx) {
+  static const double env = getenv("MZ_UPLOAD_RATIO") ? atof(getenv("MZ_UPLOAD_RATIO")) : 0.0;  // experiment knob
+  if (env >= 1.0) return env;
+  if (getenv("MZ_UPLOAD_EQUAL")) return 1.0;
+  return uploads_contended(ctx) ? kContendedRatio : 4.0;
+}
 void chunk_range(const myzkp_ctx* ctx, size_t n, int K, int pos, bool descending, size_t* lo, size_t* hi) {
-  const bool equal = uploads_contended(ctx) || getenv("MZ_UPLOAD_EQUAL");
-  const unsigned __int128 total = equal ? (unsigned __int128)K : (((unsigned __int128)1 << (2 * K)) - 1);
-  auto cum = [&](int p) {
-    const unsigned __int128 w = equal ? (unsigned __int128)p : ((((unsigned __int128)1) << (2 * p)) - 1);
-    return (size_t)(((unsigned __int128)n * w) / total);
-  };
-  size_t a = cum(pos), b = pos + 1 == K ? n : cum(pos + 1);
+  size_t a, b;
+  msm_chunk_range(n, K, pos, upload_ratio(ctx), &a, &b);
   if (descending) {
     *lo = n - b;
     *hi = n - a;
@@ -114,14 +118,22 @@ void free_ctx_scratch(myzkp_ctx* ctx) {
   for_each_scratch(ctx, [](DevBuf* b) { b->release(); });
 }
 
+}  // namespace
+
 // child i of ctx, (re)pointed at the parent's current SRS table
-int get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out) {
+int mz::get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out) {
+  if (i < 0 || i >= kMaxChildren) return fail(ctx, MYZKP_ERR_INVALID_ARG, "no such child context");
   while ((int)ctx->children.size() <= i) {
     myzkp_ctx* c = new myzkp_ctx();
     c->is_child = true;
     c->device = ctx->device;
     c->sm_count = ctx->sm_count;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the pipeline's sort streams get the highest priority: their short kernels must slip in between the blocks of
+    // the accumulate kernel that runs beside them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio = (int)ctx->children.size() >= kPipeChild0 ? prio_hi : prio_lo;
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess) {
       delete c;
       return fail(ctx, MYZKP_ERR_CUDA, "cannot create a child stream");
@@ -144,6 +156,8 @@ int get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out) {
   *out = c;
   return MYZKP_OK;
 }
+
+namespace {
 
 // MSM of n scalars that arrive in K upload chunks (events ctx->copy_ev[k]).  With u_le != NULL the
 // scalars are the quotient of the uploaded polynomial by (x - u): chunks are then consumed top first,
@@ -267,8 +281,13 @@ int myzkp_ctx_destroy(myzkp_ctx* ctx) {
   peer_release(ctx);
   free_ctx_scratch(ctx);
   for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
-    for (int i = 0; i < 6; i++)
-      if (ctx->phase_ev[s][i]) cudaEventDestroy(ctx->phase_ev[s][i]);
+    for (int k = 0; k < myzkp_ctx::kMaxPipe; k++)
+      for (int i = 0; i < 7; i++)
+        if (ctx->phase_ev[s][k][i]) cudaEventDestroy(ctx->phase_ev[s][k][i]);
+  for (int k = 0; k < 4; k++) {
+    if (ctx->pipe_sorted_ev[k]) cudaEventDestroy(ctx->pipe_sorted_ev[k]);
+    if (ctx->pipe_acc_ev[k]) cudaEventDestroy(ctx->pipe_acc_ev[k]);
+  }
   for (int i = 0; i < 8; i++)
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
   if (ctx->copy_done_ev) cudaEventDestroy(ctx->copy_done_ev);
@@ -325,9 +344,10 @@ int myzkp_ctx_enable_phase_timing(myzkp_ctx* ctx, int on) {
   if (!ctx) return MYZKP_ERR_INVALID_ARG;
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->phase_timing = on != 0;
-  if (on && !ctx->phase_ev[0][0])
+  if (on && !ctx->phase_ev[0][0][0])
     for (int s = 0; s < myzkp_ctx::kPhaseSlots; s++)
-      for (int i = 0; i < 6; i++) MZ_CUDA_TRY(ctx, cudaEventCreate(&ctx->phase_ev[s][i]));
+      for (int k = 0; k < myzkp_ctx::kMaxPipe; k++)
+        for (int i = 0; i < 7; i++) MZ_CUDA_TRY(ctx, cudaEventCreate(&ctx->phase_ev[s][k][i]));
   return MYZKP_OK;
 }
 
@@ -337,11 +357,21 @@ int myzkp_ctx_msm_phases(myzkp_ctx* ctx, int back, float out_ms[5], uint64_t out
   const int slot = (int)((ctx->msm_count - 1 - back) % myzkp_ctx::kPhaseSlots);
   for (int i = 0; i < 6; i++) out_info[i] = ctx->msm_info[slot][i];
   for (int i = 0; i < 5; i++) out_ms[i] = -1.f;
-  if (!ctx->phase_valid[slot]) return MYZKP_OK;
+  if (!ctx->phase_valid[slot] || ctx->phase_chunks[slot] < 1) return MYZKP_OK;
   MZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  MZ_CUDA_TRY(ctx, cudaEventSynchronize(ctx->phase_ev[slot][5]));
-  for (int i = 0; i < 5; i++)
-    MZ_CUDA_TRY(ctx, cudaEventElapsedTime(&out_ms[i], ctx->phase_ev[slot][i], ctx->phase_ev[slot][i + 1]));
+  auto& ev = ctx->phase_ev[slot];
+  MZ_CUDA_TRY(ctx, cudaEventSynchronize(ev[0][5]));
+  // sums over the chunks of the MSM: recode, sort (on the stream that sorted), accumulate, head merge; then the reduce
+  const int pairs[4][2] = {{0, 1}, {1, 2}, {6, 3}, {3, 4}};
+  const int chunks = ctx->phase_chunks[slot];
+  for (int i = 0; i < 4; i++) out_ms[i] = 0.f;
+  for (int k = 0; k < chunks; k++)
+    for (int i = 0; i < 4; i++) {
+      float ms = 0.f;
+      MZ_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev[k][pairs[i][0]], ev[k][pairs[i][1]]));
+      out_ms[i] += ms;
+    }
+  MZ_CUDA_TRY(ctx, cudaEventElapsedTime(&out_ms[4], ev[chunks - 1][4], ev[0][5]));
   return MYZKP_OK;
 }
 

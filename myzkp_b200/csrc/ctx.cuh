@@ -59,6 +59,10 @@ struct myzkp_ctx {
   std::vector<myzkp_ctx*> children;
   bool is_child = false;
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  // sort / accumulate pipeline of one large MSM (msm.cu: msm_xyzz): chunk k+1 is recoded and sorted on a child
+  // stream while chunk k is accumulated on this one
+  cudaEvent_t pipe_sorted_ev[4] = {}, pipe_acc_ev[4] = {};
+  int pipe_chunks = 0;  // 0 = automatic, 1 = off
 
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -90,6 +94,7 @@ struct myzkp_ctx {
   mz::DevBuf scalars2;     // quotient / folded coefficients
   mz::DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp;
   mz::DevBuf sort_parts;   // partition plan of the MSD split (msm.cu, sort.cu)
+  mz::DevBuf sort_groups;  // group starts / oversize-group tile table of the MSD sort (sort.cu)
   mz::DevBuf caller_points;  // Montgomery copies of caller-supplied points (myzkp_g1_msm)
   mz::DevBuf buckets;      // XYZZ per bucket
   mz::DevBuf heads, head_keys;
@@ -123,11 +128,17 @@ struct myzkp_ctx {
   // optional per-phase CUDA-event timing of the last MSM (bench.py roofline)
   // phases: 0 recode, 1 sort, 2 accumulate, 3 merge heads, 4 bucket reduce + tree sum
   // a ring of kPhaseSlots MSM calls so a timed loop can be read back after its final sync
+  // An MSM may run as several chunks (upload pipeline, sort / accumulate pipeline): events per chunk
+  // 0 start, 1 after recode, 2 after sort (these three on the stream that sorts - a child's in the pipelined form),
+  // 6 before accumulate, 3 after accumulate, 4 after merge (this stream); 5 = after the bucket reduce (chunk 0 only).
   static constexpr int kPhaseSlots = 32;
+  static constexpr int kMaxPipe = 4;   // chunks with their own events (and the longest sort / accumulate pipeline)
   bool phase_timing = false;
-  cudaEvent_t phase_ev[kPhaseSlots][6] = {};
+  cudaEvent_t phase_ev[kPhaseSlots][kMaxPipe][7] = {};
   bool phase_valid[kPhaseSlots] = {};
-  bool phase_pending = false;  // fill_buckets recorded events 0-4 of the current slot
+  int phase_chunks[kPhaseSlots] = {};  // chunks recorded in the slot
+  int chunk_idx = 0;                   // chunks filled since the last bucket reduce
+  bool phase_pending = false;  // fill_buckets recorded the events of the current slot
   uint64_t msm_count = 0;  // MSMs run so far (slot = count % kPhaseSlots)
   // facts about each MSM: window bits, windows, entries, segment length, segments, buckets
   uint64_t msm_info[kPhaseSlots][6] = {};
@@ -137,7 +148,7 @@ namespace mz {
 template <class F>
 inline void for_each_scratch(myzkp_ctx* ctx, F f) {
   DevBuf* bufs[] = {&ctx->scalars, &ctx->scalars2, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
-                    &ctx->sort_tmp, &ctx->sort_parts, &ctx->caller_points, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
+                    &ctx->sort_tmp, &ctx->sort_parts, &ctx->sort_groups, &ctx->caller_points, &ctx->buckets, &ctx->heads, &ctx->head_keys, &ctx->heads2,
                     &ctx->baa_pts, &ctx->baa_keys, &ctx->baa_prefix, &ctx->baa_meta, &ctx->baa_trans,
                     &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->poly_tiles, &ctx->small, &ctx->xyzz_tmp, &ctx->descs};
   for (DevBuf* b : bufs) f(b);
@@ -194,6 +205,25 @@ struct MsmItem {
   size_t n;
 };
 int msm_pick_window_batch(const myzkp_ctx* ctx, const MsmItem* items, size_t K);
+// The two halves of msm_fill_buckets_batch.  Steps 1-2 (recode, sort) run on `actx` - its stream and scratch; it may
+// be a child of `tctx`, which owns the timing slot and the non-canonical flag - and leave the sorted entries in
+// actx's scratch; steps 3-4 (accumulate, head merge) run on ctx's stream into `buckets`.
+struct SortedEntries {
+  const uint32_t* keys = nullptr;
+  const uint32_t* vals = nullptr;
+  uint64_t M = 0;   // entries
+  uint32_t nb = 0;  // buckets of the whole batch (= the sentinel key)
+  int c = 0, W = 0;
+};
+int msm_sort_entries(myzkp_ctx* actx, myzkp_ctx* tctx, int chunk, const MsmItem* items, size_t K, size_t srs_off, int c,
+                     bool per_window, SortedEntries* out);
+int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XYZZ* buckets, bool onto);
+// chunk `pos` of n scalars cut into K chunks whose sizes grow by `ratio` (1 = equal chunks)
+void msm_chunk_range(size_t n, int K, int pos, double ratio, size_t* lo, size_t* hi);
+// child i of ctx (own stream and scratch), (re)pointed at the parent's current SRS table; children 0-1 serve the
+// batched Gemini levels, kPipeChild0 and kPipeChild0 + 1 the sort / accumulate pipeline (high-priority streams)
+constexpr int kPipeChild0 = 2;
+int get_child(myzkp_ctx* ctx, int i, myzkp_ctx** out);
 int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
                            bool per_window = false, bool onto = false);
 // sum_i scalars[i] * points[i] for caller-supplied points (Montgomery affine on the device), no table of
@@ -220,6 +250,12 @@ int baa_accumulate(myzkp_ctx* ctx, const uint32_t* keys_s, const uint32_t* vals_
 int radix_sort_pairs(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
                      int bits, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts = nullptr, int P = 0,
                      bool first_pass_unordered = false);
+
+// MSD form for a list partitioned by the key bits above 8 + r (msm.cu's recode): 256-way pass + group-local sort
+int radix_sort_pairs_msd(myzkp_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint64_t n,
+                         int r, uint32_t** out_keys, uint32_t** out_vals, const uint32_t* d_parts, int P);
+void sort_set_group_cap(int cap);  // test hook: entries a group may have for the shared-memory sort (0 = default)
+int sort_group_cap();
 
 // ---- srs.cu ----
 int srs_alloc(myzkp_ctx* ctx, size_t n);

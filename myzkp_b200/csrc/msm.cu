@@ -22,6 +22,7 @@
 
 #include <vector>
 
+#include <cmath>
 #include "ctx.cuh"
 #include "inv.cuh"
 
@@ -826,6 +827,93 @@ int msm_add_buckets(myzkp_ctx* ctx, XYZZ* a, const XYZZ* b, int c) {
   return MYZKP_OK;
 }
 
+void msm_chunk_range(size_t n, int K, int pos, double ratio, size_t* lo, size_t* hi) {
+  auto cum = [&](int p) -> size_t {
+    if (p <= 0) return 0;
+    if (p >= K) return n;
+    if (ratio == 1.0) return (size_t)(((unsigned __int128)n * (unsigned)p) / (unsigned)K);
+    if (ratio == 4.0)
+      return (size_t)(((unsigned __int128)n * ((((unsigned __int128)1) << (2 * p)) - 1)) / ((((unsigned __int128)1) << (2 * K)) - 1));
+    const double f = (pow(ratio, p) - 1.0) / (pow(ratio, K) - 1.0);
+    size_t v = (size_t)((double)n * f);
+    return v > n ? n : v;
+  };
+  size_t a = cum(pos), b = cum(pos + 1);
+  if (b < a) b = a;
+  *lo = a;
+  *hi = b;
+}
+
+// Sort / accumulate pipeline of one large MSM.  The recode and the radix sort are bandwidth- and latency-bound and
+// leave the multiply pipe idle; the accumulate is bound by that pipe alone (DRAM 12 % busy).  So the scalars are cut
+// into chunks growing by kPipeRatio: chunk k+1 is recoded and sorted on a high-priority child stream (own scratch)
+// while chunk k is accumulated on this stream onto the same bucket set (msm_accumulate<kOnto>); only the small first
+// chunk's sort is exposed.  Returns the number of chunks to use for n scalars (1 = plain pipeline).
+static int pipe_chunks(const myzkp_ctx* ctx, size_t n) {
+  if (ctx->is_child) return 1;       // children are the pipeline's (and Gemini's) workers
+  if (ctx->peer_same_device) return 1;  // emulated ranks on one device (tests): scratch is frozen, keep to one stream
+  static const int env = getenv("MZ_PIPE_CHUNKS") ? atoi(getenv("MZ_PIPE_CHUNKS")) : 0;  // experiment knob
+  int K = ctx->pipe_chunks > 0 ? ctx->pipe_chunks : env;
+  if (K <= 0) K = 1;  // off by default: measured slower on B200 (profiles/experiments_r2.md)
+  if (K > myzkp_ctx::kMaxPipe) K = myzkp_ctx::kMaxPipe;
+  if ((size_t)K > n) K = 1;
+  return K;
+}
+static double pipe_ratio() {
+  static const double env = getenv("MZ_PIPE_RATIO") ? atof(getenv("MZ_PIPE_RATIO")) : 0.0;  // experiment knob
+  return env >= 1.0 ? env : 4.0;
+}
+
+static int msm_xyzz_pipelined(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, int c, int K,
+                              XYZZ* buckets) {
+  for (int k = 0; k < K; k++) {
+    if (!ctx->pipe_sorted_ev[k]) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_sorted_ev[k], cudaEventDisableTiming));
+    if (!ctx->pipe_acc_ev[k]) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_acc_ev[k], cudaEventDisableTiming));
+  }
+  if (!ctx->fork_ev) MZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));  // the scalars are ready from here on
+  const double ratio = pipe_ratio();
+  SortedEntries se[myzkp_ctx::kMaxPipe];
+  myzkp_ctx* used[2] = {nullptr, nullptr};
+  int rc = MYZKP_OK;
+  auto enqueue_sort = [&](int k) -> int {
+    myzkp_ctx* ch = nullptr;
+    MZ_TRY(get_child(ctx, kPipeChild0 + (k & 1), &ch));
+    used[k & 1] = ch;
+    // a child's scratch is free again once the accumulate of its previous chunk has run
+    MZ_CUDA_TRY(ctx, cudaStreamWaitEvent(ch->stream, k < 2 ? ctx->fork_ev : ctx->pipe_acc_ev[k - 2], 0));
+    size_t lo, hi;
+    msm_chunk_range(n, K, k, ratio, &lo, &hi);
+    MsmItem it{d_scalars + lo * 8, hi - lo};
+    int r = msm_sort_entries(ch, ctx, k, &it, 1, srs_off + lo, c, false, &se[k]);
+    if (r != MYZKP_OK && ctx->err.empty()) ctx->err = ch->err;
+    ctx->launches += ch->launches;
+    ch->launches = 0;
+    if (r != MYZKP_OK) return r;
+    MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->pipe_sorted_ev[k], ch->stream));
+    return MYZKP_OK;
+  };
+  rc = enqueue_sort(0);
+  for (int k = 0; k < K && rc == MYZKP_OK; k++) {
+    if (k + 1 < K) rc = enqueue_sort(k + 1);
+    if (rc != MYZKP_OK) break;
+    rc = cudaStreamWaitEvent(ctx->stream, ctx->pipe_sorted_ev[k], 0) == cudaSuccess ? MYZKP_OK : MYZKP_ERR_CUDA;
+    if (rc != MYZKP_OK) break;
+    rc = msm_accumulate_sorted(ctx, k, se[k], buckets, /*onto=*/k > 0);
+    if (rc != MYZKP_OK) break;
+    rc = cudaEventRecord(ctx->pipe_acc_ev[k], ctx->stream) == cudaSuccess ? MYZKP_OK : MYZKP_ERR_CUDA;
+  }
+  if (rc != MYZKP_OK) {
+    // error path: nothing of the children may still be reading the scalars or writing scratch when the caller goes on
+    for (myzkp_ctx* ch : used)
+      if (ch) cudaStreamSynchronize(ch->stream);
+    cudaGetLastError();
+    ctx->chunk_idx = 0;
+    if (ctx->err.empty()) ctx->err = "sort / accumulate pipeline failed";
+  }
+  return rc;
+}
+
 int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off, XYZZ* d_out) {
   if (n == 0) {
     xyzz_set_inf<<<1, 1, 0, ctx->stream>>>(d_out);
@@ -834,7 +922,14 @@ int msm_xyzz(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t srs_off
   }
   const int c = pick_window(ctx, n);
   MZ_CUDA_TRY(ctx, ctx->buckets.ensure(((size_t)1 << (c - 1)) * sizeof(XYZZ)));
-  MZ_TRY(msm_fill_buckets(ctx, d_scalars, n, srs_off, c, ctx->buckets.as<XYZZ>()));
+  const int Kp = pipe_chunks(ctx, n);
+  if (Kp > 1) {
+    if (srs_off + n > ctx->srs_n)
+      return fail(ctx, MYZKP_ERR_INVALID_ARG, "polynomial longer than the SRS (reference panics at polynomial.rs:162)");
+    MZ_TRY(msm_xyzz_pipelined(ctx, d_scalars, n, srs_off, c, Kp, ctx->buckets.as<XYZZ>()));
+  } else {
+    MZ_TRY(msm_fill_buckets(ctx, d_scalars, n, srs_off, c, ctx->buckets.as<XYZZ>()));
+  }
   return msm_reduce_buckets(ctx, c, ctx->buckets.as<XYZZ>(), d_out);
 }
 
@@ -887,6 +982,18 @@ int msm_fill_buckets(myzkp_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t
 // entries, not K latency-bound pipelines.
 int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_t srs_off, int c, XYZZ* buckets,
                            bool per_window, bool onto) {
+  const int chunk = ctx->chunk_idx;
+  SortedEntries se;
+  MZ_TRY(msm_sort_entries(ctx, ctx, chunk, items, K, srs_off, c, per_window, &se));
+  return msm_accumulate_sorted(ctx, chunk, se, buckets, onto);
+}
+
+#define MZ_PHASE_ON(tctx, chunk) ((tctx)->phase_timing && (tctx)->phase_ev[0][0][0] && (chunk) < myzkp_ctx::kMaxPipe)
+
+// steps 1-2: recode and sort on actx (stream, scratch); events and the non-canonical flag belong to tctx
+int msm_sort_entries(myzkp_ctx* actx, myzkp_ctx* tctx, int chunk, const MsmItem* items, size_t K, size_t srs_off, int c,
+                     bool per_window, SortedEntries* out) {
+  myzkp_ctx* ctx = actx;
   if (!ctx->table) return fail(ctx, MYZKP_ERR_NO_SRS, "no SRS loaded");
   if (c < 1 || c > 24 || (!per_window && !((ctx->windows >> c) & 1)))
     return fail(ctx, MYZKP_ERR_INVALID_ARG, "window not supported by the table");
@@ -914,18 +1021,18 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   MZ_CUDA_TRY(ctx, ctx->keys_b.ensure(M * 4));
   MZ_CUDA_TRY(ctx, ctx->vals_a.ensure(M * 4));
   MZ_CUDA_TRY(ctx, ctx->vals_b.ensure(M * 4));
-  MZ_CUDA_TRY(ctx, ctx->small.ensure(4096));
-  int* flag = reinterpret_cast<int*>(ctx->small.as<uint8_t>() + 512);
+  MZ_CUDA_TRY(tctx, tctx->small.ensure(4096));
+  int* flag = reinterpret_cast<int*>(tctx->small.as<uint8_t>() + 512);
 
   uint32_t* keys_a = ctx->keys_a.as<uint32_t>();
   uint32_t* keys_b = ctx->keys_b.as<uint32_t>();
   uint32_t* vals_a = ctx->vals_a.as<uint32_t>();
   uint32_t* vals_b = ctx->vals_b.as<uint32_t>();
 
-  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
-  const bool timing = ctx->phase_timing && ctx->phase_ev[0][0];
-#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][i], ctx->stream)); } while (0)
-  ctx->phase_valid[slot] = false;
+  const int slot = (int)(tctx->msm_count % myzkp_ctx::kPhaseSlots);
+  const bool timing = MZ_PHASE_ON(tctx, chunk);
+#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(tctx->phase_ev[slot][chunk][i], ctx->stream)); } while (0)
+  tctx->phase_valid[slot] = false;
   MZ_PHASE(0);
   // 1. recode
   const RecodeDesc* d_descs = nullptr;
@@ -937,12 +1044,25 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   }
   // MSD split inside the recode when the key has more than 16 bits (windows 20, 22, 24: the recode kernels are
   // compiled per window): the sort then only handles the low 16 (or 24) bits, inside each partition
-  int low_bits = 0, P = 0;
+  int low_bits = 0, P = 0, msd_r = 0;
   if (sort_bits > 16 && !per_window && (c == 20 || c == 22 || c == 24) && !getenv("MZ_NO_PARTITION")) {
     low_bits = 16;
     if (((uint64_t)nb >> low_bits) + 1 > (uint64_t)(kMaxParts - 3)) low_bits = 24;
+    // One polynomial: MSD sort (sort.cu: radix_sort_pairs_msd).  The partition keeps the key bits above 8 + r, a
+    // 256-way pass follows, and the groups that remain - they share all but the last r key bits - are sorted in
+    // shared memory: r is the largest value whose expected group size M / 2^(c-1-r) fits the group sort.
+    static const bool no_msd = getenv("MZ_SORT_LSD") != nullptr;  // experiment knob: the two-pass LSD form
+    if (K == 1 && !no_msd) {
+      int r = 8;
+      while (r > 4 && (M >> (c - 1 - r)) > (uint64_t)sort_group_cap() * 19 / 20) r--;
+      const int a = c - 1 - 8 - r;  // key bits decided by the partition
+      if (a >= 1 && a <= 8) {
+        msd_r = r;
+        low_bits = 8 + r;
+      }
+    }
     if (sort_bits > low_bits) P = (int)(((uint64_t)nb >> low_bits) + 1);
-    if (P < 2 || P > kMaxParts - 3) { P = 0; low_bits = 0; }
+    if (P < 2 || P > kMaxParts - 3) { P = 0; low_bits = 0; msd_r = 0; }
   }
   const uint32_t* d_parts = nullptr;
   if (n && P) {
@@ -967,9 +1087,31 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   MZ_PHASE(1);
   // 2. sort by bucket key (c bits: c-1 bucket bits + the sentinel bit; only the low bits when partitioned)
   uint32_t *keys_s = nullptr, *vals_s = nullptr;
-  MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, d_parts ? low_bits : sort_bits, &keys_s, &vals_s,
-                          d_parts, P, !getenv("MZ_SORT_STABLE")));
+  if (d_parts && msd_r)
+    MZ_TRY(radix_sort_pairs_msd(ctx, keys_a, vals_a, keys_b, vals_b, M, msd_r, &keys_s, &vals_s, d_parts, P));
+  else
+    MZ_TRY(radix_sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, M, d_parts ? low_bits : sort_bits, &keys_s, &vals_s,
+                            d_parts, P, !getenv("MZ_SORT_STABLE")));
+  MZ_PHASE(2);
+#undef MZ_PHASE
+  out->keys = keys_s;
+  out->vals = vals_s;
+  out->M = M;
+  out->nb = nb;
+  out->c = c;
+  out->W = W;
+  return MYZKP_OK;
+}
 
+// steps 3-4: accumulate the sorted entries into `buckets` and fold the segment heads, on ctx's stream
+int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XYZZ* buckets, bool onto) {
+  const uint32_t* keys_s = se.keys;
+  const uint32_t* vals_s = se.vals;
+  const uint64_t M = se.M;
+  const uint32_t nb = se.nb;
+  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
+  const bool timing = MZ_PHASE_ON(ctx, chunk);
+#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][chunk][i], ctx->stream)); } while (0)
   // 3. accumulate
   // Segment length: enough segments to fill the GPU several times over, but not much
   // shorter than the average bucket run - every extra segment inside a run costs a
@@ -993,16 +1135,31 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
     }
   }
   L += L & 1;  // even: the fused batched-affine accumulate reads (key, val) pairs as aligned 8-byte words
+  auto finish = [&](uint64_t T) {
+    ctx->msm_info[slot][0] = (uint64_t)se.c;
+    ctx->msm_info[slot][1] = (uint64_t)se.W;
+    ctx->msm_info[slot][2] = (chunk ? ctx->msm_info[slot][2] : 0) + M;
+    ctx->msm_info[slot][3] = L;
+    ctx->msm_info[slot][4] = (chunk ? ctx->msm_info[slot][4] : 0) + T;
+    ctx->msm_info[slot][5] = nb;
+    ctx->phase_valid[slot] = false;  // set by msm_reduce_buckets once event 5 is recorded
+    ctx->phase_pending = timing;
+    if (chunk < myzkp_ctx::kMaxPipe) ctx->phase_chunks[slot] = chunk + 1;
+    ctx->chunk_idx = chunk + 1;
+  };
   if (M == 0) {  // nothing but empty polynomials: every bucket is the point at infinity
     if (!onto) MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
-    ctx->phase_pending = false;
+    MZ_PHASE(6);
+    MZ_PHASE(3);
+    MZ_PHASE(4);
+    finish(0);
     return MYZKP_OK;
   }
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
   if (!onto) MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
-  MZ_PHASE(2);
+  MZ_PHASE(6);
   // Accumulate variants (myzkp_ctx_set_baa_rounds): 0 = XYZZ mixed additions only; -2 = fused batched-affine
   // pair sums (msm_accumulate_baa); -1 = automatic: fused when segments are long enough for the lane-private
   // batch inversion to amortise; 1..3 = the older multi-pass rounds (baa.cu, kept for comparison).
@@ -1064,14 +1221,7 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
   }
   MZ_PHASE(4);
 #undef MZ_PHASE
-  ctx->msm_info[slot][0] = (uint64_t)c;
-  ctx->msm_info[slot][1] = (uint64_t)W;
-  ctx->msm_info[slot][2] = M;
-  ctx->msm_info[slot][3] = L;
-  ctx->msm_info[slot][4] = T;
-  ctx->msm_info[slot][5] = nb;
-  ctx->phase_valid[slot] = false;  // set by msm_reduce_buckets once event 5 is recorded
-  ctx->phase_pending = timing;
+  finish(T);
   return MYZKP_OK;
 }
 
@@ -1079,7 +1229,7 @@ int msm_fill_buckets_batch(myzkp_ctx* ctx, const MsmItem* items, size_t K, size_
 int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, size_t K) {
   const uint32_t nb = 1u << (c - 1);
   const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
-  const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0];
+  const bool timing = ctx->phase_pending && ctx->phase_timing && ctx->phase_ev[0][0][0];
   // Level 1: chunks of Lb buckets - the kernel is two additions per bucket and nothing else.
   static const int env_lb = getenv("MZ_REDUCE_LB") ? atoi(getenv("MZ_REDUCE_LB")) : 0;        // experiment knobs
   static const int env_lb2 = getenv("MZ_REDUCE_LB2") ? atoi(getenv("MZ_REDUCE_LB2")) : 0;
@@ -1126,9 +1276,10 @@ int msm_reduce_buckets(myzkp_ctx* ctx, int c, const XYZZ* buckets, XYZZ* d_out, 
   }
   MZ_LAUNCH_CHECK(ctx);
   MZ_TRY(tree_sum(ctx, d_s, ctx->red_b.as<XYZZ>(), per_set, d_out, (uint32_t)K));
-  if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][5], ctx->stream));
+  if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][0][5], ctx->stream));
   ctx->phase_valid[slot] = timing;
   ctx->phase_pending = false;
+  ctx->chunk_idx = 0;
   ctx->msm_count++;
   return MYZKP_OK;
 }

@@ -127,3 +127,8 @@ extern "C" int myzkp_test_g1_op(myzkp_ctx* ctx, int op, const uint8_t* a, const 
   MZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return MYZKP_OK;
 }
+
+extern "C" int myzkp_test_set_sort_group_cap(int cap) {
+  mz::sort_set_group_cap(cap);
+  return MYZKP_OK;
+}

@@ -94,6 +94,7 @@ extern "C" {
     pub fn myzkp_test_field_op(ctx: *mut myzkp_ctx, field: c_int, op: c_int, a: *const u8, b: *const u8, out: *mut u8,
                                n: usize) -> c_int;
     pub fn myzkp_test_g1_op(ctx: *mut myzkp_ctx, op: c_int, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> c_int;
+    pub fn myzkp_test_set_sort_group_cap(cap: c_int) -> c_int;
 
     pub fn myzkp_device_count() -> c_int;
     pub fn myzkp_mctx_create(out: *mut *mut myzkp_mctx, device_ids: *const c_int, n_dev: c_int) -> c_int;

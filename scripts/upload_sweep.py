@@ -30,7 +30,7 @@ for lg in [int(x) for x in (sys.argv[1:] or ["19", "20", "21", "22"])]:
         ctx.commit_dev(d.data_ptr(), n, out.data_ptr())
         ctx.sync()
         best = min(best, (time.perf_counter() - t0) * 1e3)
-    print(json.dumps({"log2n": lg, "resident_ms": round(best, 3)}), flush=True)
+    print(json.dumps({"log2n": lg, "resident_ms": round(best, 3), "out": bytes(out.cpu().numpy())[:8].hex()}), flush=True)
     del d
     for k in (1, 2, 3, 4):
         ctx.set_upload_chunks(k)
@@ -41,6 +41,7 @@ for lg in [int(x) for x in (sys.argv[1:] or ["19", "20", "21", "22"])]:
             t0 = time.perf_counter()
             ctx.commit(coefs)
             best = min(best, (time.perf_counter() - t0) * 1e3)
-        res.append({"log2n": lg, "chunks": k, "ms": round(best, 3)})
+        c = ctx.commit(coefs)
+        res.append({"log2n": lg, "chunks": k, "ms": round(best, 3), "out": str(c)[:24]})
         print(json.dumps(res[-1]), flush=True)
     ctx.host_free(pinned)

@@ -146,6 +146,36 @@ def test_scalar_distributions(ctx):
     assert ctx.commit(sc) == o.fast_mul(6)  # P + P must double
 
 
+def test_msd_sort_group_paths(ctx):
+    """The large windows sort by partition -> 256-way pass -> group-local shared-memory sort (sort.cu).  With the group
+    capacity lowered, small inputs take the paths full-size inputs take: several groups per block, oversize groups
+    (skewed scalars) through the generic pass restricted to them, the sentinel partition (zero digits), empty groups."""
+    lib = ctx._lib
+    n = 1 << 14
+    alpha = 777
+    ctx.srs_generate(alpha, n)
+    rnd = random.Random(11)
+    dists = {
+        "uniform": [rnd.randrange(R) for _ in range(n)],
+        "bytes": [rnd.randrange(256) for _ in range(n)],
+        "zeros50": [0 if rnd.random() < 0.5 else rnd.randrange(R) for _ in range(n)],
+        "all_one": [1] * n,
+        "few_values": [rnd.choice([3, R - 2, 1 << 200, (1 << 253) + 12345]) for _ in range(n)],
+        "two_pow": [1 << rnd.randrange(254) for _ in range(n)],
+    }
+    exp = {name: o.expected_commit(sc, alpha) for name, sc in dists.items()}
+    try:
+        for cap in (0, 4096, 600, 64):
+            assert lib.myzkp_test_set_sort_group_cap(cap) == 0
+            for name, sc in dists.items():
+                for c in (20, 22, 24):
+                    ctx.set_msm_params(c, 0)
+                    assert ctx.commit(sc) == exp[name], (cap, name, c)
+    finally:
+        lib.myzkp_test_set_sort_group_cap(0)
+        ctx.set_msm_params(0, 0)
+
+
 def test_edge_cases_and_errors(ctx):
     alpha = 4242
     ctx.srs_generate(alpha, 8)

@@ -218,6 +218,9 @@ struct SortedEntries {
 int msm_sort_entries(myzkp_ctx* actx, myzkp_ctx* tctx, int chunk, const MsmItem* items, size_t K, size_t srs_off, int c,
                      bool per_window, SortedEntries* out);
 int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XYZZ* buckets, bool onto);
+// segments (= heads) the accumulate of n scalars at window c will use; the merge of T heads into the buckets
+uint64_t msm_segments_for(const myzkp_ctx* ctx, int c, size_t n);
+int msm_merge_heads(myzkp_ctx* ctx, XYZZ* buckets, uint32_t nb, uint64_t T);
 // chunk `pos` of n scalars cut into K chunks whose sizes grow by `ratio` (1 = equal chunks)
 void msm_chunk_range(size_t n, int K, int pos, double ratio, size_t* lo, size_t* hi);
 // child i of ctx (own stream and scratch), (re)pointed at the parent's current SRS table; children 0-1 serve the

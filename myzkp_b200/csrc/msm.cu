@@ -1103,19 +1103,9 @@ int msm_sort_entries(myzkp_ctx* actx, myzkp_ctx* tctx, int chunk, const MsmItem*
   return MYZKP_OK;
 }
 
-// steps 3-4: accumulate the sorted entries into `buckets` and fold the segment heads, on ctx's stream
-int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XYZZ* buckets, bool onto) {
-  const uint32_t* keys_s = se.keys;
-  const uint32_t* vals_s = se.vals;
-  const uint64_t M = se.M;
-  const uint32_t nb = se.nb;
-  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
-  const bool timing = MZ_PHASE_ON(ctx, chunk);
-#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][chunk][i], ctx->stream)); } while (0)
-  // 3. accumulate
-  // Segment length: enough segments to fill the GPU several times over, but not much
-  // shorter than the average bucket run - every extra segment inside a run costs a
-  // head that msm_merge_heads must fold in serially.
+// Segment length of the accumulate: enough segments to fill the GPU several times over, but not much
+// shorter than the average bucket run - every extra segment inside a run costs a head that the merge must fold in.
+static uint32_t pick_segment_len(const myzkp_ctx* ctx, uint64_t M) {
   uint32_t L = (uint32_t)ctx->segment_len;
   if (L == 0) {
     // Measured on B200 (profiles/phase_sweep_r1d.json): the head merge costs ~0.64 ns per
@@ -1135,6 +1125,54 @@ int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XY
     }
   }
   L += L & 1;  // even: the fused batched-affine accumulate reads (key, val) pairs as aligned 8-byte words
+  return L;
+}
+uint64_t msm_segments_for(const myzkp_ctx* ctx, int c, size_t n) {
+  const uint64_t M = (uint64_t)((255 + c - 1) / c) * n;
+  if (M == 0) return 0;
+  const uint32_t L = pick_segment_len(ctx, M);
+  return (M + L - 1) / L;
+}
+
+// step 4: merge T segment heads (keys in head_keys, sentinel = no head) into the buckets, level by level (levels
+// beyond the first are nearly empty unless some bucket spans more than 16 segments)
+int msm_merge_heads(myzkp_ctx* ctx, XYZZ* buckets, uint32_t nb, uint64_t T) {
+  if (T == 0) return MYZKP_OK;
+  const XYZZ* cur_heads = ctx->heads.as<XYZZ>();
+  const uint32_t* cur_keys = ctx->head_keys.as<uint32_t>();
+  uint64_t Tc = T;
+  const uint64_t T2max = (T + kMergeFan - 1) / kMergeFan;
+  const size_t lvl_stride = (((size_t)T2max * (sizeof(XYZZ) + sizeof(uint32_t)) + 255) / 256 + 1) * 256;
+  MZ_CUDA_TRY(ctx, ctx->heads2.ensure(2 * lvl_stride));
+  int pp = 0;
+  while (true) {
+    const uint64_t T2 = (Tc + kMergeFan - 1) / kMergeFan;
+    uint8_t* base = ctx->heads2.as<uint8_t>() + (size_t)pp * lvl_stride;
+    XYZZ* nh = reinterpret_cast<XYZZ*>(base);
+    uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
+    if (Tc > kMergeFan) MZ_CUDA_TRY(ctx, cudaMemsetAsync(nk, 0xff, T2 * sizeof(uint32_t), ctx->stream));
+    msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(buckets, cur_heads, cur_keys, Tc, nb, nh, nk);
+    MZ_LAUNCH_CHECK(ctx);
+    if (Tc <= kMergeFan) break;  // every head was inside the first cut: nothing was forwarded
+    cur_heads = nh;
+    cur_keys = nk;
+    Tc = T2;
+    pp ^= 1;
+  }
+  return MYZKP_OK;
+}
+
+// steps 3-4: accumulate the sorted entries into `buckets` and fold the segment heads, on ctx's stream.
+int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XYZZ* buckets, bool onto) {
+  const uint32_t* keys_s = se.keys;
+  const uint32_t* vals_s = se.vals;
+  const uint64_t M = se.M;
+  const uint32_t nb = se.nb;
+  const int slot = (int)(ctx->msm_count % myzkp_ctx::kPhaseSlots);
+  const bool timing = MZ_PHASE_ON(ctx, chunk);
+#define MZ_PHASE(i) do { if (timing) MZ_CUDA_TRY(ctx, cudaEventRecord(ctx->phase_ev[slot][chunk][i], ctx->stream)); } while (0)
+  // 3. accumulate
+  const uint32_t L = pick_segment_len(ctx, M ? M : 1);
   auto finish = [&](uint64_t T) {
     ctx->msm_info[slot][0] = (uint64_t)se.c;
     ctx->msm_info[slot][1] = (uint64_t)se.W;
@@ -1158,6 +1196,8 @@ int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XY
   const uint64_t T = (M + L - 1) / L;
   MZ_CUDA_TRY(ctx, ctx->heads.ensure(T * sizeof(XYZZ)));
   MZ_CUDA_TRY(ctx, ctx->head_keys.ensure(T * 4));
+  XYZZ* heads_p = ctx->heads.as<XYZZ>();
+  uint32_t* hkeys_p = ctx->head_keys.as<uint32_t>();
   if (!onto) MZ_CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(XYZZ), ctx->stream));
   MZ_PHASE(6);
   // Accumulate variants (myzkp_ctx_set_baa_rounds): 0 = XYZZ mixed additions only; -2 = fused batched-affine
@@ -1170,55 +1210,34 @@ int msm_accumulate_sorted(myzkp_ctx* ctx, int chunk, const SortedEntries& se, XY
     static const int minb = getenv("MZ_BAA_MINB") ? atoi(getenv("MZ_BAA_MINB")) : 4;  // experiment knob
     if (minb == 3)
       msm_accumulate_baa<3><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, heads_p, hkeys_p, T);
     else
       msm_accumulate_baa<4><<<(unsigned)((T + kAccThreads - 1) / kAccThreads), kAccThreads, 0, ctx->stream>>>(
-          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, heads_p, hkeys_p, T);
     MZ_LAUNCH_CHECK(ctx);
   } else if (baa > 0 && L >= 4) {
-    MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, buckets, ctx->heads.as<XYZZ>(),
-                          ctx->head_keys.as<uint32_t>(), T));
+    MZ_TRY(baa_accumulate(ctx, keys_s, vals_s, M, L, nb, baa, buckets, heads_p,
+                          hkeys_p, T));
   } else {
     static const bool hint64 = getenv("MZ_GATHER_L2_64B") != nullptr;  // experiment knob
     const unsigned blocks = (unsigned)((T + kAccThreads - 1) / kAccThreads);
     if (onto)
       msm_accumulate<false, true><<<blocks, kAccThreads, 0, ctx->stream>>>(
-          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, heads_p, hkeys_p, T);
     else if (hint64)
       msm_accumulate<true, false><<<blocks, kAccThreads, 0, ctx->stream>>>(
-          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, heads_p, hkeys_p, T);
     else
       msm_accumulate<false, false><<<blocks, kAccThreads, 0, ctx->stream>>>(
-          keys_s, vals_s, M, L, nb, ctx->table, buckets, ctx->heads.as<XYZZ>(), ctx->head_keys.as<uint32_t>(), T);
+          keys_s, vals_s, M, L, nb, ctx->table, buckets, heads_p, hkeys_p, T);
     MZ_LAUNCH_CHECK(ctx);
   }
 
   MZ_PHASE(3);
-  // 4. merge segment heads, level by level (levels beyond the first are nearly empty
-  //    unless some bucket spans more than 16 segments)
-  {
-    const XYZZ* cur_heads = ctx->heads.as<XYZZ>();
-    const uint32_t* cur_keys = ctx->head_keys.as<uint32_t>();
-    uint64_t Tc = T;
-    const uint64_t T2max = (T + kMergeFan - 1) / kMergeFan;
-    const size_t lvl_stride = (((size_t)T2max * (sizeof(XYZZ) + sizeof(uint32_t)) + 255) / 256 + 1) * 256;
-    MZ_CUDA_TRY(ctx, ctx->heads2.ensure(2 * lvl_stride));
-    int pp = 0;
-    while (true) {
-      const uint64_t T2 = (Tc + kMergeFan - 1) / kMergeFan;
-      uint8_t* base = ctx->heads2.as<uint8_t>() + (size_t)pp * lvl_stride;
-      XYZZ* nh = reinterpret_cast<XYZZ*>(base);
-      uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
-      if (Tc > kMergeFan) MZ_CUDA_TRY(ctx, cudaMemsetAsync(nk, 0xff, T2 * sizeof(uint32_t), ctx->stream));
-      msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(buckets, cur_heads, cur_keys, Tc, nb, nh, nk);
-      MZ_LAUNCH_CHECK(ctx);
-      if (Tc <= kMergeFan) break;  // every head was inside the first cut: nothing was forwarded
-      cur_heads = nh;
-      cur_keys = nk;
-      Tc = T2;
-      pp ^= 1;
-    }
-  }
+  // 4. merge the segment heads.  (Every chunk of the upload pipeline merges its own: the heads of several chunks
+  // cannot share one merge launch, because the same bucket then has a chain in every chunk's range and their
+  // first heads would read-modify-write it concurrently - tried, profiles/experiments_r2.md.)
+  MZ_TRY(msm_merge_heads(ctx, buckets, nb, T));
   MZ_PHASE(4);
 #undef MZ_PHASE
   finish(T);

@@ -25,7 +25,12 @@ WANT = [
 
 
 def capture(rep, source):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    import os
+    raw = rep.replace(".ncu-rep", ".raw.csv")
+    if os.path.exists(raw):  # exported on the GPU box (scripts/gpu_profiles.sh) when the report is too large to bring back
+        out = open(raw).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, vals = rows[0], rows[1], rows[2:]
     launches = []
@@ -73,11 +78,11 @@ if __name__ == "__main__":
                   "ncu --set full --clock-control none --import-source on -k regex:msm_accumulate (scripts/one_commit.py 24, 2^24 points, c=22)")
     json.dump(acc, open(f"profiles/ncu_msm_accumulate_{ROUND}.json", "w"), indent=1)
     sc = capture(f"gpurun_out/prof_sort_{ROUND}.ncu-rep",
-                 "ncu --set full --clock-control none --import-source on -k regex:sort_tile_scatter|sort_tile_hist|msm_recode "
-                 "(2^24 points, c=22, 201.3M pairs: partitioned recode, then two radix passes inside the partitions)")
+                 "ncu --set full --clock-control none --import-source on -k regex:sort_tile_scatter|sort_tile_hist|sort_group_local|msm_recode "
+                 "(2^24 points, c=22, 201.3M pairs: partitioned recode, one 256-way pass inside the partitions, group-local sort)")
     json.dump(sc, open(f"profiles/ncu_sort_{ROUND}.json", "w"), indent=1)
     rd = capture(f"gpurun_out/prof_reduce_{ROUND}.ncu-rep",
-                 "ncu --set full --clock-control none --import-source on -k regex:msm_bucket_reduce|msm_merge_level|xyzz_tree_reduce (2^24, c=22)")
+                 "ncu --set full --clock-control none --import-source on -k regex:msm_bucket_chunks|msm_bucket_reduce|msm_merge_level|xyzz_tree_reduce (2^24, c=22)")
     json.dump(rd, open(f"profiles/ncu_merge_reduce_{ROUND}.json", "w"), indent=1)
     a = acc["launches"][0]
     gb = lambda s: float(s.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[s.split()[1]]

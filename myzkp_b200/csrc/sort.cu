@@ -15,6 +15,7 @@
 // registers; peer masks come from ballots (MATCH.ANY was the bottleneck of an earlier version).
 // Stability is not needed by the MSM (bucket sums commute) but keeps the sort a plain
 // LSD radix sort whose result is independent of scheduling.
+#include <stdlib.h>
 #include "ctx.cuh"
 
 namespace mz {
@@ -240,14 +241,17 @@ __global__ void __launch_bounds__(kSortThreads) sort_tile_hist(const uint32_t* _
   }
 }
 
-// Persistent: each block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile's keys,
-// values and digit bases are fetched into registers before the current tile is ranked, so the
-// DRAM latency is covered by the ranking work rather than by occupancy.
+// Persistent: each block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  In the stable form the next tile's
+// keys, values and digit bases are fetched into registers before the current tile is ranked, so the DRAM latency is
+// covered by the ranking work rather than by occupancy; the unordered form needs fewer registers and does better
+// with a third resident block instead (kOcc).
 // kStable = false: entries of equal digit may leave in any order (allowed for a pass whose input order carries
 // no information - the first pass after the recode): ranks come from one shared-memory atomic per entry
 // instead of the ballot match and the per-warp counters, about a third of the instructions.
-template <bool kStable>
-__global__ void __launch_bounds__(kSortThreads, 2)
+// kOcc = resident blocks per SM the kernel is compiled for: 2 = with the register prefetch of the next tile; 3 / 4 = no
+// prefetch, the latency is covered by more resident warps instead (A/B on B200 in profiles/experiments_r2.md).
+template <bool kStable, int kOcc>
+__global__ void __launch_bounds__(kSortThreads, kOcc)
     sort_tile_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
                       const uint32_t* __restrict__ hist_scanned, uint32_t ntiles_arg, uint32_t* __restrict__ keys_out,
                       uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ parts, int P) {
@@ -282,14 +286,19 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     g = hist_scanned[ref.hist_base + (size_t)threadIdx.x * ref.hist_stride];
     if (parts && tn) g = g - hist_scanned[ref.first_slot] + ref.part_base;
   };
+  constexpr bool kPrefetch = kOcc <= 2;
   uint32_t tile = blockIdx.x;
-  if (tile < ntiles) fetch(tile, kn, vn, gbn);
+  if (kPrefetch && tile < ntiles) fetch(tile, kn, vn, gbn);
   for (; tile < ntiles; tile += gridDim.x) {
-    const uint32_t tile_n = tn_next;
+    if (kPrefetch) {
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) { k[i] = kn[i]; v[i] = vn[i]; }
-    gb = gbn;
-    if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x, kn, vn, gbn);  // in flight during the ranking below
+      for (int i = 0; i < kSortItems; i++) { k[i] = kn[i]; v[i] = vn[i]; }
+      gb = gbn;
+    } else {
+      fetch(tile, k, v, gb);
+    }
+    const uint32_t tile_n = kPrefetch ? tn_next : tn_next;
+    if (kPrefetch && tile + gridDim.x < ntiles) fetch(tile + gridDim.x, kn, vn, gbn);  // in flight during the ranking below
 #pragma unroll
     for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;
     gbase[threadIdx.x] = gb;
@@ -539,11 +548,18 @@ static int sort_pass(myzkp_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uin
   MZ_LAUNCH_CHECK(ctx);
   scan_apply<<<(unsigned)nchunks, kScanThreads, 0, ctx->stream>>>(hist, hist_len, sums, d_tiles);
   MZ_LAUNCH_CHECK(ctx);
-  const uint32_t sblocks = ntiles < (uint32_t)ctx->sm_count * 2 ? ntiles : (uint32_t)ctx->sm_count * 2;
-  if (!stable)
-    sort_tile_scatter<false><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+  static const int env_occ = getenv("MZ_SORT_OCC") ? atoi(getenv("MZ_SORT_OCC")) : 0;  // experiment knob
+  // unordered passes: 3 blocks per SM without the prefetch (80 registers) beat 2 with it (116): 1.29 -> 1.0 ms at 2^24
+  const int occ = stable ? 2 : (env_occ >= 2 && env_occ <= 4) ? env_occ : 3;
+  const uint32_t sblocks = ntiles < (uint32_t)(ctx->sm_count * occ) ? ntiles : (uint32_t)(ctx->sm_count * occ);
+  if (stable)
+    sort_tile_scatter<true, 2><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+  else if (occ == 4)
+    sort_tile_scatter<false, 4><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+  else if (occ == 3)
+    sort_tile_scatter<false, 3><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
   else
-    sort_tile_scatter<true><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
+    sort_tile_scatter<false, 2><<<sblocks, kSortThreads, 0, ctx->stream>>>(ki, vi, n, shift, hist, ntiles, ko, vo, d_parts, P);
   MZ_LAUNCH_CHECK(ctx);
   return MYZKP_OK;
 }

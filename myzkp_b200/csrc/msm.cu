@@ -1053,8 +1053,9 @@ int msm_sort_entries(myzkp_ctx* actx, myzkp_ctx* tctx, int chunk, const MsmItem*
     // shared memory: r is the largest value whose expected group size M / 2^(c-1-r) fits the group sort.
     static const bool no_msd = getenv("MZ_SORT_LSD") != nullptr;  // experiment knob: the two-pass LSD form
     if (K == 1 && !no_msd) {
+      static const int fill_pct = getenv("MZ_SORT_GROUP_FILL") ? atoi(getenv("MZ_SORT_GROUP_FILL")) : 95;  // experiment knob
       int r = 8;
-      while (r > 4 && (M >> (c - 1 - r)) > (uint64_t)sort_group_cap() * 19 / 20) r--;
+      while (r > 4 && (M >> (c - 1 - r)) > (uint64_t)sort_group_cap() * (uint64_t)fill_pct / 100) r--;
       const int a = c - 1 - 8 - r;  // key bits decided by the partition
       if (a >= 1 && a <= 8) {
         msd_r = r;

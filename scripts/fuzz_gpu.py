@@ -39,6 +39,7 @@ while time.time() - t0 < budget:
     ctx.set_msm_params(rnd.choice([0, 0, 4, 8, 12, 16, 20, 22, 24]), rnd.choice([0, 0, 0, 1, 2, 5, 33, 300]))
     ctx.set_upload_chunks(rnd.choice([0, 0, 1, 2, 3, 5]))
     ctx.set_baa_rounds(rnd.choice([-1, -1, -1, 1, 3]))
+    ctx._lib.myzkp_test_set_sort_group_cap(rnd.choice([0, 0, 64, 600, 4096]))  # MSD sort: oversize-group paths
     exp_c = o.expected_commit(sc, alpha)
     got_c = ctx.commit(sc)
     assert got_c == exp_c, ("commit", seed, cases, n, kind)

@@ -9,15 +9,16 @@
 //                      holds 2^(c w) P_i for every window w (rows at the bit offsets
 //                      of ctx->row_bits), every window shares ONE set of 2^(c-1)
 //                      buckets and no doublings are ever needed.
-//   2. radix sort      entries by bucket key (sort.cu: hand-written LSD radix sort,
-//                      8 bits per pass, c bits).
+//   2. radix sort      entries by bucket key (sort.cu).  Small windows: LSD passes of 8 bits.  Windows 20 / 22 / 24:
+//                      the recode leaves the entries partitioned by their high key bits, one 256-way pass and a
+//                      group-local shared-memory sort finish the job (radix_sort_pairs_msd).
 //   3. msm_accumulate  fixed-length segments of the sorted entry list, one
 //                      thread each, XYZZ mixed adds; load-balanced for any
 //                      scalar distribution (a heavy bucket just spans segments).
 //   4. msm_merge_heads segments that start inside a bucket hand their first
 //                      partial to the bucket's owner.
-//   5. msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
-//                      running sums, then a tree sum.
+//   5. msm_bucket_chunks + msm_bucket_reduce + xyzz_tree_reduce   sum_k k * B_k by chunked
+//                      running sums in two levels, then a tree sum.
 #include <stdlib.h>
 
 #include <vector>
@@ -143,13 +144,14 @@ __global__ void __launch_bounds__(256) msm_recode(RecodeDesc single, const Recod
 // ---------------------------------------------------------------------------
 // A 22-bit bucket key costs three 8-bit radix passes over 1.6 GB of entries.  The recode kernel produces
 // the entries on chip anyway, so it can do the first (most significant) split for free: partition =
-// key >> low_bits (low_bits = 16: 33 partitions for c = 22, the last one holds the zero digits), and only
-// low_bits remain for the sort, which then runs inside each partition (sort.cu, locate_tile).
+// key >> low_bits (the last partition holds the zero digits), and only low_bits remain for the sort, which then
+// runs inside each partition (sort.cu, locate_tile).  One polynomial: low_bits = 8 + r for the MSD sort (r = 7 and
+// 65 partitions at 2^24 points, c = 22); batches: low_bits = 16 (33 partitions for c = 22) and two LSD passes.
 //   msm_recode_count    per-partition entry counts (shared-memory counters, one global add per block and bin)
 //   msm_partition_plan  partition bases, tile bases, zeroed cursors (one block)
 //   msm_recode_scatter  recodes (digits stay in registers), groups the block's entries by partition in shared
 //                       memory, reserves room in every partition with one atomic add each, copies the runs out
-// Order inside a partition is arbitrary (bucket sums commute); the sort passes that follow are stable.
+// Order inside a partition is arbitrary (bucket sums commute).
 constexpr int kMaxParts = 260;
 // device layout of ctx->sort_parts (uint32): part_base[P+1] | tile_start[P+1] | counts[P] | cursor[P]
 constexpr int kSortTileEntries = 4096;  // = kSortTile of sort.cu

@@ -846,7 +846,8 @@ void msm_chunk_range(size_t n, int K, int pos, double ratio, size_t* lo, size_t*
   *hi = b;
 }
 
-// Sort / accumulate pipeline of one large MSM.  The recode and the radix sort are bandwidth- and latency-bound and
+// Sort / accumulate pipeline of one large MSM (EXPERIMENT, off by default: measured slower on B200, see pipe_chunks).
+// The recode and the radix sort are bandwidth- and latency-bound and
 // leave the multiply pipe idle; the accumulate is bound by that pipe alone (DRAM 12 % busy).  So the scalars are cut
 // into chunks growing by kPipeRatio: chunk k+1 is recoded and sorted on a high-priority child stream (own scratch)
 // while chunk k is accumulated on this stream onto the same bucket set (msm_accumulate<kOnto>); only the small first

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kSortThreads, kOcc)
     } else {
       fetch(tile, k, v, gb);
     }
-    const uint32_t tile_n = kPrefetch ? tn_next : tn_next;
+    const uint32_t tile_n = tn_next;  // set by the fetch of THIS tile (before the next one is prefetched)
     if (kPrefetch && tile + gridDim.x < ntiles) fetch(tile + gridDim.x, kn, vn, gbn);  // in flight during the ranking below
 #pragma unroll
     for (int i = 0; i < kSortWarps; i++) cnt[i][threadIdx.x] = 0;

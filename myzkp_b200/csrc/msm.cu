@@ -594,13 +594,13 @@ __global__ void __launch_bounds__(kAccThreads, kMinBlocks)
 // handful of buckets - make chains of thousands.  Chains are cut at multiples of
 // kMergeFan: the chain's first head folds the heads up to the next cut into the bucket
 // (its only writer on this level); a head sitting on a cut sums its kMergeFan-piece into a
-// slot of the next level, where the same rule applies.  Depth log_16(longest chain).
-constexpr int kMergeFan = 16;
+// slot of the next level, where the same rule applies.  Depth log_fan(longest chain); fan 16, or 8 for large inputs.
+constexpr int kMergeFanDefault = 16;
 
 __global__ void __launch_bounds__(128) msm_merge_level(XYZZ* __restrict__ buckets, const XYZZ* __restrict__ heads,
                                                        const uint32_t* __restrict__ head_keys, uint64_t T,
                                                        uint32_t sentinel, XYZZ* __restrict__ next_heads,
-                                                       uint32_t* __restrict__ next_keys) {
+                                                       uint32_t* __restrict__ next_keys, uint32_t kMergeFan) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   uint32_t k = head_keys[t];
@@ -1142,6 +1142,12 @@ uint64_t msm_segments_for(const myzkp_ctx* ctx, int c, size_t n) {
 // beyond the first are nearly empty unless some bucket spans more than 16 segments)
 int msm_merge_heads(myzkp_ctx* ctx, XYZZ* buckets, uint32_t nb, uint64_t T) {
   if (T == 0) return MYZKP_OK;
+  static const int env_fan = getenv("MZ_MERGE_FAN") ? atoi(getenv("MZ_MERGE_FAN")) : 0;  // experiment knob
+  // measured (scripts/mergefan_ab.sh): 2^24 points, 832 k heads: 0.51 / 0.38 / 0.36 ms for a fan of 16 / 8 / 4 (the top
+  // window's 34-head chains are folded serially, one lane per cut); 2^21 points, 303 k heads: 0.124 / 0.134 / 0.149 ms
+  // (the extra levels are launches of pure latency)
+  const uint32_t kMergeFan = env_fan >= 2 && env_fan <= 64 ? (uint32_t)env_fan
+                             : T >= ((uint64_t)1 << 19) ? 8u : (uint32_t)kMergeFanDefault;
   const XYZZ* cur_heads = ctx->heads.as<XYZZ>();
   const uint32_t* cur_keys = ctx->head_keys.as<uint32_t>();
   uint64_t Tc = T;
@@ -1155,7 +1161,7 @@ int msm_merge_heads(myzkp_ctx* ctx, XYZZ* buckets, uint32_t nb, uint64_t T) {
     XYZZ* nh = reinterpret_cast<XYZZ*>(base);
     uint32_t* nk = reinterpret_cast<uint32_t*>(base + (size_t)T2max * sizeof(XYZZ));
     if (Tc > kMergeFan) MZ_CUDA_TRY(ctx, cudaMemsetAsync(nk, 0xff, T2 * sizeof(uint32_t), ctx->stream));
-    msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(buckets, cur_heads, cur_keys, Tc, nb, nh, nk);
+    msm_merge_level<<<(unsigned)((Tc + 127) / 128), 128, 0, ctx->stream>>>(buckets, cur_heads, cur_keys, Tc, nb, nh, nk, kMergeFan);
     MZ_LAUNCH_CHECK(ctx);
     if (Tc <= kMergeFan) break;  // every head was inside the first cut: nothing was forwarded
     cur_heads = nh;
